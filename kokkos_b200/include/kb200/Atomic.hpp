@@ -1,0 +1,300 @@
+// kb200/Atomic.hpp -- Kokkos::atomic_* for the B200 execution space (device side).
+//
+// Same names and semantics as core/src/Kokkos_Atomics_Desul_Wrapper.hpp:72-148: every operation is
+// relaxed and device-scope (desul MemoryOrderRelaxed / MemoryScopeDevice).  The reference lowers them
+// through desul to inline PTX behind an `__isGlobal` test per call with a generic-address fallback
+// (tpls/desul/include/desul/atomics/cuda/cuda_cc7_asm_atomic_op.inc_isglobal:5-106,
+//  ...atomic_fetch_op.inc_isglobal, Compare_Exchange_CUDA.hpp) and to CAS loops / a lock array for
+// the rest (Lock_Free_Fetch_Op.hpp:23-55, Lock_Based_Fetch_Op_CUDA.hpp:20-52).
+// Here:
+//   * void ops (atomic_add/sub/min/max/and/or/xor/inc/dec) emit the no-return reduction
+//     `red.relaxed.gpu.global.<op>` (SASS RED.E.*: fire-and-forget, no result round trip) when the
+//     address is global -- one uniform __isGlobal test, as desul does -- and the generic form for
+//     team scratch in shared memory; kernels that know their operand is a View use the *_g forms;
+//   * fetch ops emit `atom.relaxed.gpu[.global].<op>`;
+//   * f64/f32 add, s/u 32/64 min/max, b32/b64 and/or/xor are native; everything else that is
+//     1,2,4 or 8 bytes goes through a CAS loop on the containing word; larger types are
+//     unsupported on this path (the reference's lock-array fallback is not reproduced).
+#ifndef KB200_ATOMIC_HPP
+#define KB200_ATOMIC_HPP
+
+#include "Macros.hpp"
+#include <type_traits>
+#include <cstring>
+
+namespace kb200 {
+namespace Impl {
+
+template <class T> struct is_i32 : std::integral_constant<bool, std::is_integral<T>::value && sizeof(T) == 4> {};
+template <class T> struct is_i64 : std::integral_constant<bool, std::is_integral<T>::value && sizeof(T) == 8> {};
+
+#define KB200_RED(NAME, PTXOP, TY, REG, CTYPE)                                                        \
+  KB200_DEVICE_FUNCTION void NAME##_g(CTYPE* p, CTYPE v) { /* p is known to be global memory */        \
+    asm volatile("red.relaxed.gpu.global." PTXOP "." TY " [%0], %1;" ::"l"(__cvta_generic_to_global(p)), REG(v) : "memory"); \
+  }                                                                                                     \
+  KB200_DEVICE_FUNCTION void NAME(CTYPE* p, CTYPE v) {                                                  \
+    if (__isGlobal(p)) {                                                                                \
+      NAME##_g(p, v);                                                                                   \
+    } else {                                                                                            \
+      asm volatile("red.relaxed.gpu." PTXOP "." TY " [%0], %1;" ::"l"(p), REG(v) : "memory");         \
+    }                                                                                                   \
+  }
+#define KB200_ATOM(NAME, PTXOP, TY, REG, CTYPE)                                                       \
+  KB200_DEVICE_FUNCTION CTYPE NAME##_g(CTYPE* p, CTYPE v) {                                             \
+    CTYPE r;                                                                                            \
+    asm volatile("atom.relaxed.gpu.global." PTXOP "." TY " %0, [%1], %2;" : "=" REG(r) : "l"(__cvta_generic_to_global(p)), REG(v) : "memory"); \
+    return r;                                                                                           \
+  }                                                                                                     \
+  KB200_DEVICE_FUNCTION CTYPE NAME(CTYPE* p, CTYPE v) {                                                 \
+    if (__isGlobal(p)) return NAME##_g(p, v);                                                           \
+    CTYPE r;                                                                                            \
+    asm volatile("atom.relaxed.gpu." PTXOP "." TY " %0, [%1], %2;" : "=" REG(r) : "l"(p), REG(v) : "memory"); \
+    return r;                                                                                           \
+  }
+// add
+KB200_RED(red_add, "add", "u32", "r", unsigned)
+KB200_RED(red_add, "add", "s32", "r", int)
+KB200_RED(red_add, "add", "u64", "l", unsigned long long)
+KB200_RED(red_add, "add", "f32", "f", float)
+KB200_RED(red_add, "add", "f64", "d", double)
+KB200_ATOM(atom_add, "add", "u32", "r", unsigned)
+KB200_ATOM(atom_add, "add", "s32", "r", int)
+KB200_ATOM(atom_add, "add", "u64", "l", unsigned long long)
+KB200_ATOM(atom_add, "add", "f32", "f", float)
+KB200_ATOM(atom_add, "add", "f64", "d", double)
+// min / max
+KB200_RED(red_min, "min", "u32", "r", unsigned)
+KB200_RED(red_min, "min", "s32", "r", int)
+KB200_RED(red_min, "min", "u64", "l", unsigned long long)
+KB200_RED(red_min, "min", "s64", "l", long long)
+KB200_RED(red_max, "max", "u32", "r", unsigned)
+KB200_RED(red_max, "max", "s32", "r", int)
+KB200_RED(red_max, "max", "u64", "l", unsigned long long)
+KB200_RED(red_max, "max", "s64", "l", long long)
+KB200_ATOM(atom_min, "min", "u32", "r", unsigned)
+KB200_ATOM(atom_min, "min", "s32", "r", int)
+KB200_ATOM(atom_min, "min", "u64", "l", unsigned long long)
+KB200_ATOM(atom_min, "min", "s64", "l", long long)
+KB200_ATOM(atom_max, "max", "u32", "r", unsigned)
+KB200_ATOM(atom_max, "max", "s32", "r", int)
+KB200_ATOM(atom_max, "max", "u64", "l", unsigned long long)
+KB200_ATOM(atom_max, "max", "s64", "l", long long)
+// bitwise
+KB200_RED(red_and, "and", "b32", "r", unsigned)
+KB200_RED(red_and, "and", "b64", "l", unsigned long long)
+KB200_RED(red_or, "or", "b32", "r", unsigned)
+KB200_RED(red_or, "or", "b64", "l", unsigned long long)
+KB200_RED(red_xor, "xor", "b32", "r", unsigned)
+KB200_RED(red_xor, "xor", "b64", "l", unsigned long long)
+KB200_ATOM(atom_and, "and", "b32", "r", unsigned)
+KB200_ATOM(atom_and, "and", "b64", "l", unsigned long long)
+KB200_ATOM(atom_or, "or", "b32", "r", unsigned)
+KB200_ATOM(atom_or, "or", "b64", "l", unsigned long long)
+KB200_ATOM(atom_xor, "xor", "b32", "r", unsigned)
+KB200_ATOM(atom_xor, "xor", "b64", "l", unsigned long long)
+KB200_ATOM(atom_exch, "exch", "b32", "r", unsigned)
+KB200_ATOM(atom_exch, "exch", "b64", "l", unsigned long long)
+#undef KB200_RED
+#undef KB200_ATOM
+
+KB200_DEVICE_FUNCTION unsigned atom_cas(unsigned* p, unsigned cmp, unsigned val) {
+  unsigned r;
+  asm volatile("atom.relaxed.gpu.cas.b32 %0, [%1], %2, %3;" : "=r"(r) : "l"(p), "r"(cmp), "r"(val) : "memory");
+  return r;
+}
+KB200_DEVICE_FUNCTION unsigned long long atom_cas(unsigned long long* p, unsigned long long cmp, unsigned long long val) {
+  unsigned long long r;
+  asm volatile("atom.relaxed.gpu.cas.b64 %0, [%1], %2, %3;" : "=l"(r) : "l"(p), "l"(cmp), "l"(val) : "memory");
+  return r;
+}
+KB200_DEVICE_FUNCTION unsigned short atom_cas(unsigned short* p, unsigned short cmp, unsigned short val) {
+  unsigned short r;
+  asm volatile("atom.relaxed.gpu.cas.b16 %0, [%1], %2, %3;" : "=h"(r) : "l"(p), "h"(cmp), "h"(val) : "memory");
+  return r;
+}
+
+// the unsigned word type an object of SIZE bytes is operated on as
+template <int SIZE> struct word_of;
+template <> struct word_of<2> { using type = unsigned short; };
+template <> struct word_of<4> { using type = unsigned; };
+template <> struct word_of<8> { using type = unsigned long long; };
+
+template <class T, class W = typename word_of<sizeof(T)>::type>
+KB200_DEVICE_FUNCTION W as_word(T v) { W w; memcpy(&w, &v, sizeof(T)); return w; }
+template <class T, class W>
+KB200_DEVICE_FUNCTION T from_word(W w) { T v; memcpy(&v, &w, sizeof(T)); return v; }
+
+// generic RMW through compare-and-swap (desul Lock_Free_Fetch_Op.hpp:23-55 plays this role);
+// returns the value before the update.  1-byte objects use the enclosing aligned 16-bit word.
+template <class T, class F>
+KB200_DEVICE_FUNCTION T cas_loop(T* p, F f) {
+  static_assert(sizeof(T) == 1 || sizeof(T) == 2 || sizeof(T) == 4 || sizeof(T) == 8,
+                "kb200 atomics support 1,2,4,8-byte types (no lock-array fallback)");
+  if constexpr (sizeof(T) == 1) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    unsigned short* wp = reinterpret_cast<unsigned short*>(a & ~uintptr_t(1));
+    const int shift = (a & 1) * 8;
+    unsigned short old = *reinterpret_cast<volatile unsigned short*>(wp), assumed;
+    T before;
+    do {
+      assumed = old;
+      unsigned char b = (unsigned char)(assumed >> shift);
+      memcpy(&before, &b, 1);
+      T after = f(before);
+      unsigned char nb;
+      memcpy(&nb, &after, 1);
+      unsigned short nw = (unsigned short)((assumed & ~(0xffu << shift)) | ((unsigned)nb << shift));
+      old = atom_cas(wp, assumed, nw);
+    } while (old != assumed);
+    return before;
+  } else {
+    using W = typename word_of<sizeof(T)>::type;
+    W* wp = reinterpret_cast<W*>(p);
+    W old = *reinterpret_cast<volatile W*>(wp), assumed;
+    do {
+      assumed = old;
+      old = atom_cas(wp, assumed, as_word<T>(f(from_word<T, W>(assumed))));
+    } while (old != assumed);
+    return from_word<T, W>(old);
+  }
+}
+
+// map a C++ integer type onto the PTX-typed overload set
+template <class T> struct native_int { using type = void; };
+template <> struct native_int<int> { using type = int; };
+template <> struct native_int<unsigned> { using type = unsigned; };
+template <> struct native_int<long> { using type = long long; };
+template <> struct native_int<unsigned long> { using type = unsigned long long; };
+template <> struct native_int<long long> { using type = long long; };
+template <> struct native_int<unsigned long long> { using type = unsigned long long; };
+template <class T> using native_int_t = typename native_int<T>::type;
+template <class T> using native_uint_t = typename word_of<sizeof(T)>::type;
+template <class T> constexpr bool has_native_int = !std::is_void<native_int_t<T>>::value;
+
+}  // namespace Impl
+
+// ------------------------------------------------------------------ public API (device side)
+template <class T>
+KB200_DEVICE_FUNCTION void atomic_add(T* p, T v) {
+  if constexpr (std::is_same<T, double>::value || std::is_same<T, float>::value || std::is_same<T, int>::value ||
+                std::is_same<T, unsigned>::value) {
+    Impl::red_add(p, v);
+  } else if constexpr (Impl::has_native_int<T> && sizeof(T) == 8) {  // two's complement: signed add == unsigned add
+    Impl::red_add(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+  } else {
+    Impl::cas_loop(p, [=](T o) { return (T)(o + v); });
+  }
+}
+template <class T>
+KB200_DEVICE_FUNCTION T atomic_fetch_add(T* p, T v) {
+  if constexpr (std::is_same<T, double>::value || std::is_same<T, float>::value || std::is_same<T, int>::value ||
+                std::is_same<T, unsigned>::value) {
+    return Impl::atom_add(p, v);
+  } else if constexpr (Impl::has_native_int<T> && sizeof(T) == 8) {
+    return (T)Impl::atom_add(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+  } else {
+    return Impl::cas_loop(p, [=](T o) { return (T)(o + v); });
+  }
+}
+template <class T> KB200_DEVICE_FUNCTION void atomic_sub(T* p, T v) {
+  if constexpr (std::is_integral<T>::value && (sizeof(T) == 4 || sizeof(T) == 8)) atomic_add(p, (T)(T(0) - v));
+  else if constexpr (std::is_floating_point<T>::value) atomic_add(p, -v);
+  else Impl::cas_loop(p, [=](T o) { return (T)(o - v); });
+}
+template <class T> KB200_DEVICE_FUNCTION T atomic_fetch_sub(T* p, T v) {
+  if constexpr (std::is_integral<T>::value && (sizeof(T) == 4 || sizeof(T) == 8)) return atomic_fetch_add(p, (T)(T(0) - v));
+  else if constexpr (std::is_floating_point<T>::value) return atomic_fetch_add(p, -v);
+  else return Impl::cas_loop(p, [=](T o) { return (T)(o - v); });
+}
+template <class T> KB200_DEVICE_FUNCTION void atomic_inc(T* p) { atomic_add(p, T(1)); }
+template <class T> KB200_DEVICE_FUNCTION void atomic_dec(T* p) { atomic_sub(p, T(1)); }
+template <class T> KB200_DEVICE_FUNCTION void atomic_increment(T* p) { atomic_add(p, T(1)); }
+template <class T> KB200_DEVICE_FUNCTION void atomic_decrement(T* p) { atomic_sub(p, T(1)); }
+template <class T> KB200_DEVICE_FUNCTION T atomic_fetch_inc(T* p) { return atomic_fetch_add(p, T(1)); }
+template <class T> KB200_DEVICE_FUNCTION T atomic_fetch_dec(T* p) { return atomic_fetch_sub(p, T(1)); }
+
+#define KB200_MINMAX(NAME, FETCHNAME, RED, ATOM, CMP)                                              \
+  template <class T>                                                                               \
+  KB200_DEVICE_FUNCTION void NAME(T* p, T v) {                                                      \
+    if constexpr (Impl::has_native_int<T>) Impl::RED(reinterpret_cast<Impl::native_int_t<T>*>(p), (Impl::native_int_t<T>)v); \
+    else Impl::cas_loop(p, [=](T o) { return (v CMP o) ? v : o; });                                 \
+  }                                                                                                 \
+  template <class T>                                                                               \
+  KB200_DEVICE_FUNCTION T FETCHNAME(T* p, T v) {                                                    \
+    if constexpr (Impl::has_native_int<T>) return (T)Impl::ATOM(reinterpret_cast<Impl::native_int_t<T>*>(p), (Impl::native_int_t<T>)v); \
+    else return Impl::cas_loop(p, [=](T o) { return (v CMP o) ? v : o; });                          \
+  }
+KB200_MINMAX(atomic_min, atomic_fetch_min, red_min, atom_min, <)
+KB200_MINMAX(atomic_max, atomic_fetch_max, red_max, atom_max, >)
+#undef KB200_MINMAX
+
+#define KB200_BITOP(NAME, FETCHNAME, RED, ATOM, OP)                                                 \
+  template <class T>                                                                               \
+  KB200_DEVICE_FUNCTION void NAME(T* p, T v) {                                                      \
+    if constexpr (std::is_integral<T>::value && (sizeof(T) == 4 || sizeof(T) == 8))                 \
+      Impl::RED(reinterpret_cast<Impl::native_uint_t<T>*>(p), (Impl::native_uint_t<T>)v);            \
+    else Impl::cas_loop(p, [=](T o) { return (T)(o OP v); });                                       \
+  }                                                                                                 \
+  template <class T>                                                                               \
+  KB200_DEVICE_FUNCTION T FETCHNAME(T* p, T v) {                                                    \
+    if constexpr (std::is_integral<T>::value && (sizeof(T) == 4 || sizeof(T) == 8))                 \
+      return (T)Impl::ATOM(reinterpret_cast<Impl::native_uint_t<T>*>(p), (Impl::native_uint_t<T>)v); \
+    else return Impl::cas_loop(p, [=](T o) { return (T)(o OP v); });                                \
+  }
+KB200_BITOP(atomic_and, atomic_fetch_and, red_and, atom_and, &)
+KB200_BITOP(atomic_or, atomic_fetch_or, red_or, atom_or, |)
+KB200_BITOP(atomic_xor, atomic_fetch_xor, red_xor, atom_xor, ^)
+#undef KB200_BITOP
+
+template <class T> KB200_DEVICE_FUNCTION T atomic_fetch_mul(T* p, T v) { return Impl::cas_loop(p, [=](T o) { return (T)(o * v); }); }
+template <class T> KB200_DEVICE_FUNCTION T atomic_fetch_div(T* p, T v) { return Impl::cas_loop(p, [=](T o) { return (T)(o / v); }); }
+template <class T> KB200_DEVICE_FUNCTION void atomic_mul(T* p, T v) { (void)atomic_fetch_mul(p, v); }
+template <class T> KB200_DEVICE_FUNCTION void atomic_div(T* p, T v) { (void)atomic_fetch_div(p, v); }
+
+template <class T>
+KB200_DEVICE_FUNCTION T atomic_exchange(T* p, T v) {
+  if constexpr (sizeof(T) == 4 || sizeof(T) == 8) {
+    using W = typename Impl::word_of<sizeof(T)>::type;
+    return Impl::from_word<T, W>(Impl::atom_exch(reinterpret_cast<W*>(p), Impl::as_word<T>(v)));
+  } else {
+    return Impl::cas_loop(p, [=](T) { return v; });
+  }
+}
+template <class T>
+KB200_DEVICE_FUNCTION T atomic_compare_exchange(T* p, T compare, T v) {
+  if constexpr (sizeof(T) == 2 || sizeof(T) == 4 || sizeof(T) == 8) {
+    using W = typename Impl::word_of<sizeof(T)>::type;
+    return Impl::from_word<T, W>(Impl::atom_cas(reinterpret_cast<W*>(p), Impl::as_word<T>(compare), Impl::as_word<T>(v)));
+  } else {
+    return Impl::cas_loop(p, [=](T o) { return o == compare ? v : o; });
+  }
+}
+template <class T>
+KB200_DEVICE_FUNCTION T atomic_load(const T* p) {
+  static_assert(sizeof(T) <= 8, "");
+  if constexpr (sizeof(T) == 8) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return Impl::from_word<T, unsigned long long>(w);
+  } else if constexpr (sizeof(T) == 4) {
+    unsigned w;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(p) : "memory");
+    return Impl::from_word<T, unsigned>(w);
+  } else {
+    return *reinterpret_cast<const volatile T*>(p);
+  }
+}
+template <class T>
+KB200_DEVICE_FUNCTION void atomic_store(T* p, T v) {
+  static_assert(sizeof(T) <= 8, "");
+  if constexpr (sizeof(T) == 8) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(Impl::as_word<T>(v)) : "memory");
+  } else if constexpr (sizeof(T) == 4) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(Impl::as_word<T>(v)) : "memory");
+  } else {
+    *reinterpret_cast<volatile T*>(p) = v;
+  }
+}
+
+}  // namespace kb200
+#endif

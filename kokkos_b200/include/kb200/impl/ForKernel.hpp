@@ -1,0 +1,79 @@
+// kb200/impl/ForKernel.hpp -- the elementwise (parallel_for) skeleton of the B200 execution space.
+//
+// Replaces ParallelFor<F,RangePolicy,Cuda>::operator()/execute
+// (core/src/Cuda/Kokkos_Cuda_Parallel_Range.hpp:72-112: one element per thread, 8-byte accesses,
+// ~10^6 tiny blocks for N=2^28).  Here each thread handles UNROLL units per tile with all loads
+// issued before the first store; a typed body moves 32 bytes per unit (LDG/STG.E.ENL2.256).
+//
+// Body concept (device side):
+//   using packet = ...;
+//   packet load(int64 u) const;                // issue the loads of unit u
+//   void   store(const packet&, int64 u) const;// compute + store unit u
+//   int64  edge_count() const;   void edge(int64 k) const;   // scalar head/tail elements
+#ifndef KB200_IMPL_FORKERNEL_HPP
+#define KB200_IMPL_FORKERNEL_HPP
+
+#include "HostRuntime.hpp"
+
+namespace kb200 {
+namespace Impl {
+
+template <class Body, int BLOCK, int UNROLL>
+__global__ void __launch_bounds__(BLOCK) range_for_kernel(const __grid_constant__ Body body, const int64 n_units) {
+  constexpr int64 TILE = (int64)BLOCK * UNROLL;
+  const int64 full_tiles = n_units / TILE;
+  for (int64 tile = blockIdx.x; tile < full_tiles; tile += gridDim.x) {
+    const int64 base = tile * TILE + threadIdx.x;
+    typename Body::packet p[UNROLL];
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j) p[j] = body.load(base + (int64)j * BLOCK);
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j) body.store(p[j], base + (int64)j * BLOCK);
+  }
+  if ((int64)blockIdx.x == full_tiles % gridDim.x) {
+    for (int64 u = full_tiles * TILE + threadIdx.x; u < n_units; u += BLOCK) {
+      typename Body::packet p = body.load(u);
+      body.store(p, u);
+    }
+  }
+  const int64 edges = body.edge_count();
+  for (int64 k = (int64)blockIdx.x * BLOCK + threadIdx.x; k < edges; k += (int64)gridDim.x * BLOCK) body.edge(k);
+}
+
+template <class Body, int BLOCK = 256, int UNROLL = 4>
+struct RangeForLaunch {
+  static int resident_blocks_per_sm() {
+    static int cached = 0;
+    if (cached == 0) {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, range_for_kernel<Body, BLOCK, UNROLL>, BLOCK, 0);
+      cached = nb > 0 ? nb : 1;
+    }
+    return cached;
+  }
+  // waves <= 0: one block per tile (plain grid); waves > 0: persistent grid of SMs*resident*waves/… blocks
+  static int run(b200_instance* inst, const Body& body, int64 n_units, int blocks_per_sm_cap = 0) {
+    static_assert(sizeof(Body) <= 32000, "closure exceeds the kernel parameter space");
+    HostRuntime rt(inst);
+    constexpr int64 TILE = (int64)BLOCK * UNROLL;
+    int64 tiles = (n_units + TILE - 1) / TILE;
+    if (tiles < 1) {
+      if (body.edge_count() == 0) return 0;  // empty range: nothing to launch
+      tiles = 1;
+    }
+    int64 grid = tiles;
+    if (blocks_per_sm_cap > 0) {
+      int bps = resident_blocks_per_sm();
+      if (blocks_per_sm_cap < bps) bps = blocks_per_sm_cap;
+      const int64 cap = (int64)rt.sm_count() * bps;
+      if (grid > cap) grid = cap;
+    }
+    if (grid > 0x7fffffffll) grid = 0x7fffffffll;
+    range_for_kernel<Body, BLOCK, UNROLL><<<(unsigned)grid, BLOCK, 0, rt.stream()>>>(body, n_units);
+    return rt.check_launch("kb200::range_for_kernel");
+  }
+};
+
+}  // namespace Impl
+}  // namespace kb200
+#endif
