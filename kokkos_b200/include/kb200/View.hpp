@@ -1,0 +1,318 @@
+// kb200/View.hpp -- View<T*>-style device allocations for the B200 execution space.
+//
+// Covers what the hot path needs of core/src/Kokkos_View.hpp + core/src/Cuda/Kokkos_CudaSpace.{hpp,cpp}:
+//   * View<T>, View<T*>, View<T**>, View<T***>  (rank 0..3, run-time extents), LayoutLeft / LayoutRight,
+//     memory spaces B200Space (device, CudaSpace::allocate -> b200_malloc) and HostSpace,
+//     MemoryTraits<Unmanaged> / pointer-wrapping constructors, labels, ref-counted ownership
+//     (impl/Kokkos_SharedAlloc.*), zero-initialisation at allocation (View/Kokkos_ViewAlloc.hpp:100-166 ->
+//     ZeroMemset<B200> = b200_memset_async + fence), WithoutInitializing;
+//   * deep_copy between spaces / from a scalar, create_mirror_view[_and_copy], subview of rank-1 ranges.
+// Device Views default to LayoutLeft as in the reference's Cuda backend (first index fastest).
+// Everything rank>3, strided layouts, static extents and DualView/DynRankView are out of scope
+// (SURVEY.md section 2 rows 11, 24).
+#ifndef KB200_VIEW_HPP
+#define KB200_VIEW_HPP
+
+#include "B200.hpp"
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <utility>
+
+namespace kb200 {
+
+struct LayoutLeft {};
+struct LayoutRight {};
+struct HostSpace {
+  using memory_space = HostSpace;
+  static constexpr const char* name() { return "Host"; }
+};
+struct B200Space {
+  using memory_space = B200Space;
+  using execution_space = B200;
+  static constexpr const char* name() { return "B200"; }
+};
+struct B200HostPinnedSpace {  // CudaHostPinnedSpace: host memory the device can read/write
+  using memory_space = B200HostPinnedSpace;
+  static constexpr const char* name() { return "B200HostPinned"; }
+};
+enum MemoryTraitsFlags { Unmanaged = 1, RandomAccess = 2, Atomic = 4, Restrict = 8 };
+template <unsigned F>
+struct MemoryTraits { static constexpr unsigned flags = F; };
+using MemoryUnmanaged = MemoryTraits<Unmanaged>;
+
+struct WithoutInitializing_t {};
+constexpr WithoutInitializing_t WithoutInitializing{};
+struct ViewAllocProp {  // view_alloc(WithoutInitializing, "label")
+  std::string label;
+  bool init = true;
+  const B200* space = nullptr;
+};
+inline ViewAllocProp view_alloc(WithoutInitializing_t, const std::string& l) { return ViewAllocProp{l, false, nullptr}; }
+inline ViewAllocProp view_alloc(const std::string& l, WithoutInitializing_t) { return ViewAllocProp{l, false, nullptr}; }
+inline ViewAllocProp view_alloc(const std::string& l) { return ViewAllocProp{l, true, nullptr}; }
+inline ViewAllocProp view_alloc(const B200& s, const std::string& l) { return ViewAllocProp{l, true, &s}; }
+inline ViewAllocProp view_alloc(const B200& s, WithoutInitializing_t, const std::string& l) { return ViewAllocProp{l, false, &s}; }
+
+namespace Impl {
+template <class D> struct data_type_rank { static constexpr int value = 0; using type = D; };
+template <class D> struct data_type_rank<D*> { static constexpr int value = 1 + data_type_rank<D>::value; using type = typename data_type_rank<D>::type; };
+
+template <class... P> struct view_props;
+template <> struct view_props<> {
+  using layout = void; using space = void; static constexpr unsigned traits = 0;
+};
+template <class First, class... Rest>
+struct view_props<First, Rest...> {
+  using next = view_props<Rest...>;
+  static constexpr bool is_layout = std::is_same<First, LayoutLeft>::value || std::is_same<First, LayoutRight>::value;
+  static constexpr bool is_space = std::is_same<First, HostSpace>::value || std::is_same<First, B200Space>::value ||
+                                   std::is_same<First, B200HostPinnedSpace>::value || std::is_same<First, B200>::value;
+  using layout = std::conditional_t<is_layout, First, typename next::layout>;
+  using space_raw = std::conditional_t<is_space, First, typename next::space>;
+  using space = std::conditional_t<std::is_same<space_raw, B200>::value, B200Space, space_raw>;
+  template <class T, class = void> struct flags_of { static constexpr unsigned value = 0; };
+  template <class T> struct flags_of<T, std::void_t<decltype(T::flags)>> { static constexpr unsigned value = T::flags; };
+  static constexpr unsigned traits = flags_of<First>::value | next::traits;
+};
+
+// host-side allocation record (SharedAllocationRecord's role); never dereferenced on the device
+struct AllocRecord {
+  int refcount = 1;
+  void* ptr = nullptr;
+  int kind = 0;  // 0 device, 1 host malloc, 2 host pinned
+  std::shared_ptr<b200_instance> inst;
+  std::string label;
+};
+inline void release(AllocRecord* r) {
+  if (!r) return;
+  if (__atomic_sub_fetch(&r->refcount, 1, __ATOMIC_ACQ_REL) == 0) {
+    if (r->ptr) {
+      if (r->kind == 0) b200_free(r->inst.get(), r->ptr);
+      else if (r->kind == 1) std::free(r->ptr);
+      else b200_free_host_pinned(r->ptr);
+    }
+    delete r;
+  }
+}
+}  // namespace Impl
+
+template <class DataType, class... Props>
+class View {
+  using props = Impl::view_props<Props...>;
+
+ public:
+  static constexpr int rank = Impl::data_type_rank<DataType>::value;
+  static_assert(rank <= 3, "kb200::View supports rank 0..3");
+  using value_type = typename Impl::data_type_rank<DataType>::type;
+  using non_const_value_type = std::remove_const_t<value_type>;
+  using memory_space = std::conditional_t<std::is_void<typename props::space>::value, B200Space, typename props::space>;
+  using array_layout = std::conditional_t<std::is_void<typename props::layout>::value,
+                                          std::conditional_t<std::is_same<memory_space, HostSpace>::value, LayoutRight, LayoutLeft>,
+                                          typename props::layout>;
+  using execution_space = B200;
+  using size_type = size_t;
+  using pointer_type = value_type*;
+  using reference_type = value_type&;
+  static constexpr bool is_managed = !(props::traits & Unmanaged);
+  static constexpr bool is_device = !std::is_same<memory_space, HostSpace>::value;
+  using HostMirror = View<std::remove_const_t<DataType>, array_layout, HostSpace>;
+  using non_const_type = View<DataType, Props...>;
+
+  KB200_INLINE_FUNCTION View() : m_data(nullptr), m_rec(nullptr) { m_ext[0] = m_ext[1] = m_ext[2] = 0; }
+
+  // allocating constructors
+  explicit View(const std::string& label, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0) { allocate(ViewAllocProp{label, true, nullptr}, n0, n1, n2); }
+  explicit View(const char* label, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0) { allocate(ViewAllocProp{label, true, nullptr}, n0, n1, n2); }
+  explicit View(const ViewAllocProp& p, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0) { allocate(p, n0, n1, n2); }
+  // wrapping (unmanaged) constructor
+  KB200_INLINE_FUNCTION View(pointer_type ptr, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0) : m_data(ptr), m_rec(nullptr) {
+    set_extents(n0, n1, n2);
+  }
+
+  KB200_INLINE_FUNCTION View(const View& o) : m_data(o.m_data), m_rec(o.m_rec) { copy_ext(o); retain(); }
+  KB200_INLINE_FUNCTION View(View&& o) noexcept : m_data(o.m_data), m_rec(o.m_rec) { copy_ext(o); o.m_rec = nullptr; o.m_data = nullptr; }
+  // const-adding / trait-changing conversions between compatible Views
+  template <class D2, class... P2, class = std::enable_if_t<std::is_convertible<typename View<D2, P2...>::pointer_type, pointer_type>::value &&
+                                                            View<D2, P2...>::rank == rank>>
+  KB200_INLINE_FUNCTION View(const View<D2, P2...>& o) : m_data(o.data()), m_rec(is_managed ? o.impl_record() : nullptr) {
+    m_ext[0] = o.extent(0); m_ext[1] = o.extent(1); m_ext[2] = o.extent(2);
+    retain();
+  }
+  KB200_INLINE_FUNCTION View& operator=(const View& o) {
+    if (this != &o) { drop(); m_data = o.m_data; m_rec = o.m_rec; copy_ext(o); retain(); }
+    return *this;
+  }
+  KB200_INLINE_FUNCTION View& operator=(View&& o) noexcept {
+    if (this != &o) { drop(); m_data = o.m_data; m_rec = o.m_rec; copy_ext(o); o.m_rec = nullptr; o.m_data = nullptr; }
+    return *this;
+  }
+  KB200_INLINE_FUNCTION ~View() { drop(); }
+
+  // element access
+  template <int R = rank, std::enable_if_t<R == 0, int> = 0>
+  KB200_FORCEINLINE_FUNCTION reference_type operator()() const { return *m_data; }
+  template <class I0, int R = rank, std::enable_if_t<R == 1, int> = 0>
+  KB200_FORCEINLINE_FUNCTION reference_type operator()(const I0 i0) const { return m_data[i0]; }
+  template <class I0, int R = rank, std::enable_if_t<R == 1, int> = 0>
+  KB200_FORCEINLINE_FUNCTION reference_type operator[](const I0 i0) const { return m_data[i0]; }
+  template <class I0, class I1, int R = rank, std::enable_if_t<R == 2, int> = 0>
+  KB200_FORCEINLINE_FUNCTION reference_type operator()(const I0 i0, const I1 i1) const {
+    if constexpr (std::is_same<array_layout, LayoutLeft>::value) return m_data[(size_t)i0 + m_ext[0] * (size_t)i1];
+    else return m_data[(size_t)i1 + m_ext[1] * (size_t)i0];
+  }
+  template <class I0, class I1, class I2, int R = rank, std::enable_if_t<R == 3, int> = 0>
+  KB200_FORCEINLINE_FUNCTION reference_type operator()(const I0 i0, const I1 i1, const I2 i2) const {
+    if constexpr (std::is_same<array_layout, LayoutLeft>::value) return m_data[(size_t)i0 + m_ext[0] * ((size_t)i1 + m_ext[1] * (size_t)i2)];
+    else return m_data[(size_t)i2 + m_ext[2] * ((size_t)i1 + m_ext[1] * (size_t)i0)];
+  }
+
+  KB200_FORCEINLINE_FUNCTION pointer_type data() const { return m_data; }
+  KB200_FORCEINLINE_FUNCTION size_t extent(int r) const { return r < rank ? m_ext[r] : 1; }
+  KB200_FORCEINLINE_FUNCTION int extent_int(int r) const { return (int)extent(r); }
+  KB200_FORCEINLINE_FUNCTION size_t size() const {
+    size_t s = 1;
+    for (int r = 0; r < rank; ++r) s *= m_ext[r];
+    return s;
+  }
+  KB200_FORCEINLINE_FUNCTION size_t span() const { return size(); }
+  KB200_FORCEINLINE_FUNCTION constexpr bool span_is_contiguous() const { return true; }
+  KB200_FORCEINLINE_FUNCTION bool is_allocated() const { return m_data != nullptr; }
+  KB200_FORCEINLINE_FUNCTION size_t stride(int r) const {
+    if (std::is_same<array_layout, LayoutLeft>::value) { size_t s = 1; for (int k = 0; k < r; ++k) s *= m_ext[k]; return s; }
+    size_t s = 1; for (int k = rank - 1; k > r; --k) s *= m_ext[k]; return s;
+  }
+  std::string label() const { return m_rec ? m_rec->label : std::string(); }
+  int use_count() const { return m_rec ? m_rec->refcount : 0; }
+  KB200_INLINE_FUNCTION Impl::AllocRecord* impl_record() const { return m_rec; }
+
+ private:
+  KB200_INLINE_FUNCTION void set_extents(size_t n0, size_t n1, size_t n2) {
+    m_ext[0] = rank > 0 ? n0 : 1; m_ext[1] = rank > 1 ? n1 : 1; m_ext[2] = rank > 2 ? n2 : 1;
+  }
+  KB200_INLINE_FUNCTION void copy_ext(const View& o) { m_ext[0] = o.m_ext[0]; m_ext[1] = o.m_ext[1]; m_ext[2] = o.m_ext[2]; }
+  KB200_INLINE_FUNCTION void retain() {
+#ifndef __CUDA_ARCH__
+    if (m_rec) __atomic_add_fetch(&m_rec->refcount, 1, __ATOMIC_RELAXED);
+#endif
+  }
+  KB200_INLINE_FUNCTION void drop() {
+#ifndef __CUDA_ARCH__
+    if (m_rec) { Impl::release(m_rec); m_rec = nullptr; }
+#endif
+  }
+  void allocate(const ViewAllocProp& p, size_t n0, size_t n1, size_t n2) {
+    static_assert(!std::is_const<value_type>::value, "cannot allocate a View of const");
+    set_extents(n0, n1, n2);
+    const size_t bytes = size() * sizeof(value_type);
+    m_rec = new Impl::AllocRecord();
+    m_rec->label = p.label;
+    void* ptr = nullptr;
+    if (std::is_same<memory_space, B200Space>::value) {
+      B200 space = p.space ? *p.space : B200();
+      m_rec->inst = Impl::default_instance();
+      m_rec->kind = 0;
+      if (p.space) m_rec->inst = std::shared_ptr<b200_instance>(std::shared_ptr<b200_instance>(), space.impl_instance());
+      int rc = b200_malloc(space.impl_instance(), bytes, &ptr);
+      if (rc) { delete m_rec; m_rec = nullptr; Impl::throw_on_error(rc); }
+      if (p.init && bytes) {  // value-initialisation of trivially constructible types = zero memset + fence
+        Impl::throw_on_error(b200_memset_async(space.impl_instance(), ptr, 0, bytes));
+        space.fence("kb200::View: fence after zero-initialisation");
+      }
+    } else if (std::is_same<memory_space, B200HostPinnedSpace>::value) {
+      m_rec->kind = 2;
+      int rc = b200_malloc_host_pinned(bytes, &ptr);
+      if (rc) { delete m_rec; m_rec = nullptr; Impl::throw_on_error(rc); }
+      if (p.init && bytes) std::memset(ptr, 0, bytes);
+    } else {
+      m_rec->kind = 1;
+      if (bytes) {
+        ptr = p.init ? std::calloc(bytes, 1) : std::malloc(bytes);
+        if (!ptr) { delete m_rec; m_rec = nullptr; throw RawMemoryAllocationFailure("kb200::View: host allocation failed"); }
+      }
+    }
+    m_rec->ptr = ptr;
+    m_data = static_cast<pointer_type>(ptr);
+  }
+
+  pointer_type m_data;
+  size_t m_ext[3];
+  Impl::AllocRecord* m_rec;
+};
+
+template <class T> struct is_view : std::false_type {};
+template <class D, class... P> struct is_view<View<D, P...>> : std::true_type {};
+template <class T> constexpr bool is_view_v = is_view<std::decay_t<T>>::value;
+
+// ---------------------------------------------------------------- subview (rank-1 ranges)
+template <class D, class... P, class I0, class I1>
+View<D, P...> subview(const View<D, P...>& v, const std::pair<I0, I1>& r) {
+  static_assert(View<D, P...>::rank == 1, "kb200::subview: rank-1 Views only");
+  if ((size_t)r.second > v.extent(0) || (size_t)r.first > (size_t)r.second) throw std::runtime_error("kb200::subview: range out of bounds");
+  View<D, P...> s(v);  // shares ownership
+  struct Access : View<D, P...> {};  // keep the allocation alive, re-point the window
+  View<D, P...> w(v.data() + r.first, (size_t)(r.second - r.first));
+  // an unmanaged window plus a keep-alive copy would double the handle; the window alone is enough when the parent
+  // outlives it (the reference's subviews share the record: emulate by copying the record pointer)
+  return Impl_subview_attach(w, s);
+}
+template <class V>
+V Impl_subview_attach(V& window, const V& owner) {
+  V out(owner);                      // retains the record
+  std::memcpy((void*)&out, (void*)&window, offsetof_data_ext<V>());  // overwrite pointer + extents, keep record
+  return out;
+}
+template <class V>
+constexpr size_t offsetof_data_ext() { return sizeof(void*) + 3 * sizeof(size_t); }
+
+// ---------------------------------------------------------------- deep_copy
+namespace Impl {
+template <class DstSpace, class SrcSpace>
+inline void copy_bytes(const B200& space, void* dst, const void* src, size_t bytes) {
+  constexpr bool dd = !std::is_same<DstSpace, HostSpace>::value && !std::is_same<DstSpace, B200HostPinnedSpace>::value;
+  constexpr bool sd = !std::is_same<SrcSpace, HostSpace>::value && !std::is_same<SrcSpace, B200HostPinnedSpace>::value;
+  if (bytes == 0) return;
+  if (dd && sd) throw_on_error(b200_memcpy_d2d_async(space.impl_instance(), dst, src, bytes));
+  else if (dd) throw_on_error(b200_memcpy_h2d_async(space.impl_instance(), dst, src, bytes));
+  else if (sd) throw_on_error(b200_memcpy_d2h_async(space.impl_instance(), dst, src, bytes));
+  else std::memcpy(dst, src, bytes);
+}
+}  // namespace Impl
+
+// deep_copy(dst, src): same extents, same layout, contiguous (core/src/Kokkos_CopyViews.hpp:897-1100 fast path);
+// blocking, like the reference's two-argument form
+template <class D1, class... P1, class D2, class... P2>
+void deep_copy(const B200& space, const View<D1, P1...>& dst, const View<D2, P2...>& src) {
+  using V1 = View<D1, P1...>; using V2 = View<D2, P2...>;
+  static_assert(std::is_same<typename V1::non_const_value_type, typename V2::non_const_value_type>::value, "deep_copy: value types differ");
+  static_assert(V1::rank == V2::rank, "deep_copy: ranks differ");
+  static_assert(V1::rank <= 1 || std::is_same<typename V1::array_layout, typename V2::array_layout>::value,
+                "deep_copy: layouts differ (no transposing copy on this path)");
+  for (int r = 0; r < V1::rank; ++r)
+    if (dst.extent(r) != src.extent(r)) throw std::runtime_error("kb200::deep_copy: extents differ");
+  Impl::copy_bytes<typename V1::memory_space, typename V2::memory_space>(space, (void*)dst.data(), (const void*)src.data(),
+                                                                         dst.size() * sizeof(typename V1::value_type));
+}
+template <class D1, class... P1, class D2, class... P2>
+void deep_copy(const View<D1, P1...>& dst, const View<D2, P2...>& src) {
+  B200 space;
+  deep_copy(space, dst, src);
+  space.fence("kb200::deep_copy: fence after copy");
+}
+
+template <class D, class... P>
+typename View<D, P...>::HostMirror create_mirror_view(const View<D, P...>& v) {
+  return typename View<D, P...>::HostMirror(view_alloc(WithoutInitializing, v.label() + "_mirror"), v.extent(0), v.extent(1), v.extent(2));
+}
+template <class D, class... P>
+typename View<D, P...>::HostMirror create_mirror(const View<D, P...>& v) { return create_mirror_view(v); }
+template <class Space, class D, class... P>
+auto create_mirror_view_and_copy(const Space&, const View<D, P...>& v) {
+  using Dst = View<std::remove_const_t<D>, typename View<D, P...>::array_layout, typename Space::memory_space>;
+  Dst d(view_alloc(WithoutInitializing, v.label() + "_copy"), v.extent(0), v.extent(1), v.extent(2));
+  deep_copy(d, v);
+  return d;
+}
+
+}  // namespace kb200
+#endif

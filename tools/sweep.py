@@ -37,8 +37,11 @@ def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     log2n = int(sys.argv[2]) if len(sys.argv) > 2 else 28
     torch.cuda.set_device(0)
-    stream = torch.cuda.current_stream().cuda_stream
-    space = kb.B200(0, stream=stream)
+    # torch's default stream has handle 0 (= "make me a new stream" for b200_instance_create):
+    # run everything on an explicit side stream so the CUDA events bracket our kernels
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    space = kb.B200(0, stream=side.cuda_stream)
     n = 1 << log2n
     out = {}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
