@@ -88,11 +88,14 @@ typedef enum {
   B200_SCRATCH_RESULT = 2,   /* pinned+mapped host slot the last block writes the result to */
   B200_SCRATCH_FUNCTOR = 3,  /* device: closure spill for functors larger than 4 KiB        */
   B200_SCRATCH_TEAM_L1 = 4,  /* device: level-1 team scratch arena                          */
-  B200_SCRATCH_SCAN_DESC = 5 /* device: look-back tile descriptors (epoch tagged, never cleared) */
+  B200_SCRATCH_SCAN_DESC = 5,  /* device: 16-byte look-back tile descriptors (epoch tagged, never cleared) */
+  B200_SCRATCH_SCAN_STATUS = 6,/* device: 8-byte status words of the generic scan (epoch tagged, never cleared) */
+  B200_SCRATCH_SCAN_VALUES = 7 /* device: aggregate/inclusive value slots of the generic scan             */
 } b200_scratch_kind;
 int b200_scratch_get(b200_instance* inst, int kind, size_t bytes, void** dev_ptr, void** host_ptr);
-/* reserve `ntiles` look-back tiles: returns the epoch to tag descriptors with and the value the
- * monotonic tile counter has at the start of this launch */
+/* start a look-back launch: returns the epoch to tag descriptors with and the device tile-id counter
+ * (counter_dev[0] = next tile id, reset to 0 by the last CTA of the launch; counter_dev[1] = finished CTAs);
+ * counter_base is always 0 and kept for ABI stability */
 int b200_scan_begin(b200_instance* inst, uint64_t ntiles, uint64_t* epoch, uint64_t* counter_base,
                     unsigned long long** counter_dev);
 /* one call for everything a reduction launch needs: partials (>= partial_bytes), the ticket word,

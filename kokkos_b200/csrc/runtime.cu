@@ -151,6 +151,8 @@ int b200_finalize(b200_instance* I) {
   if (I->result_ring) cudaFreeHost(I->result_ring);
   if (I->scan_desc) cudaFree(I->scan_desc);
   if (I->tile_counter) cudaFree(I->tile_counter);
+  if (I->scan_status) cudaFree(I->scan_status);
+  if (I->scan_values) cudaFree(I->scan_values);
   if (I->functor_spill) cudaFree(I->functor_spill);
   if (I->team_l1) cudaFree(I->team_l1);
   if (I->owns_stream && I->stream) cudaStreamDestroy(I->stream);
@@ -285,6 +287,14 @@ int b200_scratch_get(b200_instance* I, int kind, size_t bytes, void** dev_ptr, v
       if ((rc = grow(I, &I->scan_desc, &I->scan_desc_bytes, bytes, true, "b200_scratch_get(scan_desc)"))) return rc;
       *dev_ptr = I->scan_desc;
       return 0;
+    case B200_SCRATCH_SCAN_STATUS:
+      if ((rc = grow(I, &I->scan_status, &I->scan_status_bytes, bytes < (4u << 20) ? (4u << 20) : bytes, true, "b200_scratch_get(scan_status)"))) return rc;
+      *dev_ptr = I->scan_status;
+      return 0;
+    case B200_SCRATCH_SCAN_VALUES:
+      if ((rc = grow(I, &I->scan_values, &I->scan_values_bytes, bytes < (8u << 20) ? (8u << 20) : bytes, false, "b200_scratch_get(scan_values)"))) return rc;
+      *dev_ptr = I->scan_values;
+      return 0;
   }
   return b200_set_error(B200_EINVAL, "b200_scratch_get", "unknown scratch kind");
 }
@@ -316,9 +326,11 @@ int b200_scan_begin(b200_instance* I, uint64_t ntiles, uint64_t* epoch, uint64_t
   if (!I) return b200_set_error(B200_ENOTINIT, "b200_scan_begin", nullptr);
   if (!epoch || !counter_base || !counter_dev) return b200_set_error(B200_EINVAL, "b200_scan_begin", "NULL out pointer");
   std::lock_guard<std::mutex> lock(I->mutex);
+  // counter_dev[0] hands out tile ids and is reset to 0 by the last CTA of each launch (counter_dev[1] counts
+  // finished CTAs), so a launch that fails on the host cannot desynchronise host and device state.
+  (void)ntiles;
   *epoch = ++I->scan_epoch;
-  *counter_base = I->tiles_issued;
-  I->tiles_issued += ntiles;
+  *counter_base = 0;
   *counter_dev = I->tile_counter;
   return 0;
 }

@@ -34,6 +34,11 @@ struct b200_instance {
   uint64_t scan_epoch = 0;
   uint64_t tiles_issued = 0;
 
+  void* scan_status = nullptr;
+  size_t scan_status_bytes = 0;
+  void* scan_values = nullptr;
+  size_t scan_values_bytes = 0;
+
   void* functor_spill = nullptr;
   size_t functor_spill_bytes = 0;
   void* team_l1 = nullptr;

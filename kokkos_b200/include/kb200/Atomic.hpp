@@ -173,7 +173,8 @@ template <class T> constexpr bool has_native_int = !std::is_void<native_int_t<T>
 
 }  // namespace Impl
 
-// ------------------------------------------------------------------ public API (device side)
+namespace Impl {
+namespace dev {  // device implementations
 template <class T>
 KB200_DEVICE_FUNCTION void atomic_add(T* p, T v) {
   if constexpr (std::is_same<T, double>::value || std::is_same<T, float>::value || std::is_same<T, int>::value ||
@@ -294,6 +295,69 @@ KB200_DEVICE_FUNCTION void atomic_store(T* p, T v) {
   } else {
     *reinterpret_cast<volatile T*>(p) = v;
   }
+}
+
+}  // namespace dev
+}  // namespace Impl
+
+// ------------------------------------------------------------------ public API
+// __host__ __device__ like Kokkos::atomic_* (they are called from KB200_LAMBDA functors).  The device pass is the
+// PTX above; the host pass (host-space Views in host code) uses the compiler's __atomic builtins.
+namespace Impl {
+template <class T, class F>
+inline T host_rmw(T* p, F f) {
+  T old, nw;
+  __atomic_load(p, &old, __ATOMIC_RELAXED);
+  do { nw = f(old); } while (!__atomic_compare_exchange(p, &old, &nw, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+  return old;
+}
+}  // namespace Impl
+#ifdef __CUDA_ARCH__
+#define KB200_ATOMIC_DISPATCH(DEV, HOST) DEV
+#else
+#define KB200_ATOMIC_DISPATCH(DEV, HOST) HOST
+#endif
+#define KB200_ATOMIC_BINARY(NAME, FETCH, EXPR)                                                                         \
+  template <class T>                                                                                                   \
+  KB200_FORCEINLINE_FUNCTION void NAME(T* p, std::common_type_t<T> v) {                                                 \
+    KB200_ATOMIC_DISPATCH(Impl::dev::NAME(p, v);, (void)Impl::host_rmw(p, [=](T o) { return (T)(EXPR); });)             \
+  }                                                                                                                    \
+  template <class T>                                                                                                   \
+  KB200_FORCEINLINE_FUNCTION T FETCH(T* p, std::common_type_t<T> v) {                                                   \
+    KB200_ATOMIC_DISPATCH(return Impl::dev::FETCH(p, v);, return Impl::host_rmw(p, [=](T o) { return (T)(EXPR); });)    \
+  }
+KB200_ATOMIC_BINARY(atomic_add, atomic_fetch_add, o + v)
+KB200_ATOMIC_BINARY(atomic_sub, atomic_fetch_sub, o - v)
+KB200_ATOMIC_BINARY(atomic_min, atomic_fetch_min, v < o ? v : o)
+KB200_ATOMIC_BINARY(atomic_max, atomic_fetch_max, v > o ? v : o)
+KB200_ATOMIC_BINARY(atomic_and, atomic_fetch_and, o & v)
+KB200_ATOMIC_BINARY(atomic_or, atomic_fetch_or, o | v)
+KB200_ATOMIC_BINARY(atomic_xor, atomic_fetch_xor, o ^ v)
+KB200_ATOMIC_BINARY(atomic_mul, atomic_fetch_mul, o * v)
+KB200_ATOMIC_BINARY(atomic_div, atomic_fetch_div, o / v)
+#undef KB200_ATOMIC_BINARY
+template <class T> KB200_FORCEINLINE_FUNCTION void atomic_inc(T* p) { atomic_add(p, T(1)); }
+template <class T> KB200_FORCEINLINE_FUNCTION void atomic_dec(T* p) { atomic_sub(p, T(1)); }
+template <class T> KB200_FORCEINLINE_FUNCTION void atomic_increment(T* p) { atomic_add(p, T(1)); }
+template <class T> KB200_FORCEINLINE_FUNCTION void atomic_decrement(T* p) { atomic_sub(p, T(1)); }
+template <class T> KB200_FORCEINLINE_FUNCTION T atomic_fetch_inc(T* p) { return atomic_fetch_add(p, T(1)); }
+template <class T> KB200_FORCEINLINE_FUNCTION T atomic_fetch_dec(T* p) { return atomic_fetch_sub(p, T(1)); }
+template <class T>
+KB200_FORCEINLINE_FUNCTION T atomic_exchange(T* p, std::common_type_t<T> v) {
+  KB200_ATOMIC_DISPATCH(return Impl::dev::atomic_exchange(p, v);, return Impl::host_rmw(p, [=](T) { return v; });)
+}
+template <class T>
+KB200_FORCEINLINE_FUNCTION T atomic_compare_exchange(T* p, std::common_type_t<T> compare, std::common_type_t<T> v) {
+  KB200_ATOMIC_DISPATCH(return Impl::dev::atomic_compare_exchange(p, compare, v);,
+                        return Impl::host_rmw(p, [=](T o) { return o == compare ? v : o; });)
+}
+template <class T>
+KB200_FORCEINLINE_FUNCTION T atomic_load(const T* p) {
+  KB200_ATOMIC_DISPATCH(return Impl::dev::atomic_load(p);, T v; __atomic_load(p, &v, __ATOMIC_RELAXED); return v;)
+}
+template <class T>
+KB200_FORCEINLINE_FUNCTION void atomic_store(T* p, std::common_type_t<T> v) {
+  KB200_ATOMIC_DISPATCH(Impl::dev::atomic_store(p, v);, __atomic_store(p, &v, __ATOMIC_RELAXED);)
 }
 
 }  // namespace kb200

@@ -1,0 +1,280 @@
+// kb200/Parallel.hpp -- front-end of the hot path: kb200::parallel_for / parallel_reduce / parallel_scan
+// over RangePolicy and MDRangePolicy, generic in the user functor (compiled by nvcc in the user's TU).
+//
+// Same call forms as core/src/Kokkos_Parallel.hpp:130-173,348-454 and the parallel_reduce overload set of
+// core/src/Kokkos_Parallel_Reduce.hpp:1679-1837: optional label, policy or plain count, functor, and for
+// reductions a scalar reference / rank-0 View / reducer object.  Functor analysis follows
+// core/src/impl/Kokkos_FunctorAnalysis.hpp:865-958: value_type from the result argument, optional
+// functor members init / join / final, work tag passed as first argument.
+//
+// What executes is not the reference's design:
+//   ParallelFor   -> impl/ForKernel.hpp     (UNROLL independent iterations per thread, persistent-free grid)
+//   ParallelReduce-> impl/ReduceKernel.hpp  (register partials, shuffle/redux.sync, ticketed ordered combine,
+//                                            result written to a mapped pinned slot)
+//   ParallelScan  -> impl/ScanGeneric.hpp   (single pass, decoupled look-back; functor called exactly twice
+//                                            per index: final=false for its contribution, final=true once)
+//   MDRange       -> impl/MDRangeKernel.hpp (tile = thread block, hardware threadIdx gives the in-tile
+//                                            coordinates: no div/mod per element)
+// Scalar results block (fence) and View/device results do not, as in the reference
+// (Kokkos_Parallel_Reduce.hpp:1592-1638).
+#ifndef KB200_PARALLEL_HPP
+#define KB200_PARALLEL_HPP
+
+#include "Policy.hpp"
+#include "Reducers.hpp"
+#include "View.hpp"
+#include "impl/ForKernel.hpp"
+#include "impl/ReduceKernel.hpp"
+#include "impl/ScanGeneric.hpp"
+#include "impl/MDRangeKernel.hpp"
+
+namespace kb200 {
+namespace Impl {
+
+// ---- invoke a functor with or without a work tag --------------------------------------------------
+template <class Tag, class F, class... Args>
+KB200_FORCEINLINE_FUNCTION void invoke(const F& f, Args&&... args) {
+  if constexpr (std::is_void<Tag>::value) f(static_cast<Args&&>(args)...);
+  else f(Tag{}, static_cast<Args&&>(args)...);
+}
+
+// ---- functor analysis: does the functor bring its own init / join / final ? -----------------------
+template <class F, class V, class = void> struct has_join : std::false_type {};
+template <class F, class V> struct has_join<F, V, std::void_t<decltype(std::declval<const F&>().join(std::declval<V&>(), std::declval<const V&>()))>> : std::true_type {};
+template <class F, class V, class = void> struct has_init : std::false_type {};
+template <class F, class V> struct has_init<F, V, std::void_t<decltype(std::declval<const F&>().init(std::declval<V&>()))>> : std::true_type {};
+template <class F, class V, class = void> struct has_final : std::false_type {};
+template <class F, class V> struct has_final<F, V, std::void_t<decltype(std::declval<const F&>().final(std::declval<V&>()))>> : std::true_type {};
+template <class Tag, class F, class V, class = void> struct has_tagged_join : std::false_type {};
+template <class Tag, class F, class V>
+struct has_tagged_join<Tag, F, V, std::void_t<decltype(std::declval<const F&>().join(std::declval<Tag>(), std::declval<V&>(), std::declval<const V&>()))>> : std::true_type {};
+
+// Uniform init/join/final over "functor with optional members" (default: value-init and operator+=,
+// FunctorAnalysis.hpp:604-613,724-732) -- the reducer used when the result argument is a plain scalar or View.
+template <class F, class V, class Tag>
+struct FunctorReducer {
+  using value_type = V;
+  F f;
+  KB200_FORCEINLINE_FUNCTION void init(V& v) const {
+    if constexpr (has_init<F, V>::value) f.init(v); else v = V();
+  }
+  KB200_FORCEINLINE_FUNCTION void join(V& d, const V& s) const {
+    if constexpr (!std::is_void<Tag>::value && has_tagged_join<Tag, F, V>::value) f.join(Tag{}, d, s);
+    else if constexpr (has_join<F, V>::value) f.join(d, s);
+    else d += s;
+  }
+  KB200_FORCEINLINE_FUNCTION void final(V& v) const {
+    if constexpr (has_final<F, V>::value) f.final(v);
+  }
+};
+// plain-old-data fast case: no functor copy inside the reducer, and redux.sync for 32-bit integers
+template <class V>
+struct DefaultSumReducer {
+  using value_type = V;
+  static constexpr int redux_op = ReduxAdd;
+  KB200_FORCEINLINE_FUNCTION void init(V& v) const { v = V(); }
+  KB200_FORCEINLINE_FUNCTION void join(V& d, const V& s) const { d += s; }
+  KB200_FORCEINLINE_FUNCTION void final(V&) const {}
+};
+// wrap a reducer object (built-in or user-defined: has ::reducer, value_type, init, join, maybe final)
+template <class R>
+struct ReducerAdapter {
+  using value_type = typename R::value_type;
+  R r;
+  template <class Q, class = void> struct has_redux : std::false_type {};
+  template <class Q> struct has_redux<Q, std::void_t<decltype(Q::redux_op)>> : std::true_type {};
+  KB200_FORCEINLINE_FUNCTION void init(value_type& v) const { r.init(v); }
+  KB200_FORCEINLINE_FUNCTION void join(value_type& d, const value_type& s) const { r.join(d, s); }
+  KB200_FORCEINLINE_FUNCTION void final(value_type& v) const {
+    if constexpr (has_final<R, value_type>::value) r.final(v);
+  }
+};
+template <class R>
+struct redux_op_of<ReducerAdapter<R>, void> { static constexpr int value = redux_op_of<R>::value; };
+
+// ---- bodies adapting a Kokkos functor to the kernel skeletons -----------------------------------------
+struct EmptyPacket {};
+template <class F, class Tag, class Index>
+struct FunctorForBody {
+  using packet = EmptyPacket;
+  F f;
+  Index begin;
+  KB200_DEVICE_FUNCTION packet load(int64) const { return packet{}; }
+  KB200_DEVICE_FUNCTION void store(const packet&, int64 u) const { invoke<Tag>(f, (Index)(begin + (Index)u)); }
+  KB200_FUNCTION int64 edge_count() const { return 0; }
+  KB200_DEVICE_FUNCTION void edge(int64) const {}
+};
+template <class F, class Tag, class Index, class V>
+struct FunctorReduceBody {
+  using packet = EmptyPacket;
+  F f;
+  Index begin;
+  KB200_DEVICE_FUNCTION packet load(int64) const { return packet{}; }
+  KB200_DEVICE_FUNCTION void consume(const packet&, int64 u, V& acc) const { invoke<Tag>(f, (Index)(begin + (Index)u), acc); }
+  KB200_FUNCTION int64 edge_count() const { return 0; }
+  KB200_DEVICE_FUNCTION void edge(int64, V&) const {}
+};
+
+// ---- where does a reduction result go ----------------------------------------------------------------
+template <class V>
+struct ResultTarget { V* host; V* dev; };
+template <class V>
+ResultTarget<V> target_of_scalar(V& v) { return ResultTarget<V>{&v, nullptr}; }
+template <class ViewT>
+ResultTarget<typename ViewT::non_const_value_type> target_of_view(const ViewT& v) {
+  using V = typename ViewT::non_const_value_type;
+  if (ViewT::is_device) return ResultTarget<V>{nullptr, (V*)v.data()};
+  return ResultTarget<V>{(V*)v.data(), nullptr};  // host View: written after a fence, like a scalar
+}
+
+}  // namespace Impl
+
+// =====================================================================================================
+// parallel_for
+// =====================================================================================================
+template <class... P, class F>
+void parallel_for(const std::string& /*label*/, const RangePolicy<P...>& policy, const F& f) {
+  using Policy = RangePolicy<P...>;
+  using Body = Impl::FunctorForBody<F, typename Policy::work_tag, typename Policy::index_type>;
+  const int64 n = (int64)(policy.end() - policy.begin());
+  if (n <= 0) return;
+  Body body{f, policy.begin()};
+  Impl::throw_on_error(Impl::RangeForLaunch<Body, 256, 4>::run(policy.space().impl_instance(), body, n, 0));
+}
+template <class... P, class F>
+void parallel_for(const RangePolicy<P...>& policy, const F& f) { parallel_for(std::string(), policy, f); }
+template <class F, class = std::enable_if_t<!std::is_class<std::decay_t<F>>::value || true>>
+void parallel_for(const std::string& label, size_t n, const F& f) { parallel_for(label, RangePolicy<>(0, (long long)n), f); }
+template <class F>
+void parallel_for(size_t n, const F& f) { parallel_for(std::string(), RangePolicy<>(0, (long long)n), f); }
+
+template <class... P, class F>
+void parallel_for(const std::string& /*label*/, const MDRangePolicy<P...>& policy, const F& f) {
+  Impl::throw_on_error(Impl::MDRangeFor<MDRangePolicy<P...>, F>::run(policy, f));
+}
+template <class... P, class F>
+void parallel_for(const MDRangePolicy<P...>& policy, const F& f) { parallel_for(std::string(), policy, f); }
+
+// =====================================================================================================
+// parallel_reduce
+// =====================================================================================================
+namespace Impl {
+template <class Policy, class F, class Red>
+void reduce_dispatch(const Policy& policy, const F& f, const Red& red, ResultTarget<typename Red::value_type> t);
+
+template <class... P, class F, class Red>
+void reduce_dispatch(const RangePolicy<P...>& policy, const F& f, const Red& red, ResultTarget<typename Red::value_type> t) {
+  using Policy = RangePolicy<P...>;
+  using V = typename Red::value_type;
+  using Body = FunctorReduceBody<F, typename Policy::work_tag, typename Policy::index_type, V>;
+  int64 n = (int64)(policy.end() - policy.begin());
+  if (n < 0) n = 0;
+  Body body{f, policy.begin()};
+  // wider unroll for small values: more independent loads in flight per thread
+  constexpr int UNROLL = sizeof(V) <= 8 ? 8 : (sizeof(V) <= 32 ? 4 : 2);
+  throw_on_error(RangeReduceLaunch<Body, Red, 256, UNROLL>::run(policy.space().impl_instance(), body, red, n, t.host, t.dev));
+}
+template <class... P, class F, class Red>
+void reduce_dispatch(const MDRangePolicy<P...>& policy, const F& f, const Red& red, ResultTarget<typename Red::value_type> t) {
+  throw_on_error(MDRangeReduce<MDRangePolicy<P...>, F, Red>::run(policy, f, red, t.host, t.dev));
+}
+
+template <class T> struct is_policy : std::false_type {};
+template <class... P> struct is_policy<RangePolicy<P...>> : std::true_type {};
+template <class... P> struct is_policy<MDRangePolicy<P...>> : std::true_type {};
+template <class... P> struct is_policy<TeamPolicy<P...>> : std::true_type {};
+
+template <class Policy, class F, class R>
+void reduce_entry(const Policy& policy, const F& f, R&& result) {
+  using RD = std::decay_t<R>;
+  using Tag = typename Policy::work_tag;
+  if constexpr (is_reducer_v<RD>) {
+    using V = typename RD::value_type;
+    ReducerAdapter<RD> red{result};
+    ResultTarget<V> t = result.references_scalar() ? ResultTarget<V>{&result.reference(), nullptr}
+                                                   : ResultTarget<V>{nullptr, &result.reference()};
+    reduce_dispatch(policy, f, red, t);
+  } else if constexpr (is_view_v<RD>) {
+    using V = typename RD::non_const_value_type;
+    static_assert(RD::rank == 0, "parallel_reduce: View results must be rank 0 (array reductions are not on this path)");
+    if constexpr (has_join<F, V>::value || has_init<F, V>::value || has_final<F, V>::value) {
+      reduce_dispatch(policy, f, FunctorReducer<F, V, Tag>{f}, target_of_view(result));
+    } else {
+      reduce_dispatch(policy, f, DefaultSumReducer<V>{}, target_of_view(result));
+    }
+  } else {
+    using V = RD;
+    static_assert(!std::is_const<std::remove_reference_t<R>>::value, "parallel_reduce: result must be a non-const reference");
+    if constexpr (has_join<F, V>::value || has_init<F, V>::value || has_final<F, V>::value) {
+      reduce_dispatch(policy, f, FunctorReducer<F, V, Tag>{f}, target_of_scalar(result));
+    } else {
+      reduce_dispatch(policy, f, DefaultSumReducer<V>{}, target_of_scalar(result));
+    }
+  }
+}
+}  // namespace Impl
+
+template <class Policy, class F, class R, class = std::enable_if_t<Impl::is_policy<Policy>::value>>
+void parallel_reduce(const std::string& /*label*/, const Policy& policy, const F& f, R&& result) {
+  Impl::reduce_entry(policy, f, static_cast<R&&>(result));
+}
+template <class Policy, class F, class R, class = std::enable_if_t<Impl::is_policy<Policy>::value>>
+void parallel_reduce(const Policy& policy, const F& f, R&& result) {
+  Impl::reduce_entry(policy, f, static_cast<R&&>(result));
+}
+template <class F, class R>
+void parallel_reduce(const std::string& /*label*/, size_t n, const F& f, R&& result) {
+  Impl::reduce_entry(RangePolicy<>(0, (long long)n), f, static_cast<R&&>(result));
+}
+template <class F, class R>
+void parallel_reduce(size_t n, const F& f, R&& result) {
+  Impl::reduce_entry(RangePolicy<>(0, (long long)n), f, static_cast<R&&>(result));
+}
+
+// =====================================================================================================
+// parallel_scan (RangePolicy)
+// =====================================================================================================
+namespace Impl {
+// value type of a nested-scan lambda f(i, T& partial, bool final): deduced from its call operator
+template <class L, class I>
+struct scan_arg_of {
+  template <class C, class R, class A0, class A1, class A2> static A1 pick(R (C::*)(A0, A1, A2) const);
+  template <class C, class R, class A0, class A1, class A2> static A1 pick(R (C::*)(A0, A1, A2));
+  using type = decltype(pick(&L::operator()));
+};
+template <class F, class = void> struct scan_value_type_of {};
+template <class F> struct scan_value_type_of<F, std::void_t<typename F::value_type>> { using type = typename F::value_type; };
+}  // namespace Impl
+
+// value type deduced from the total argument
+template <class... P, class F, class V, class = std::enable_if_t<!is_view_v<V>>>
+void parallel_scan(const std::string& /*label*/, const RangePolicy<P...>& policy, const F& f, V& total) {
+  using Policy = RangePolicy<P...>;
+  using Red = Impl::FunctorReducer<F, V, typename Policy::work_tag>;
+  Impl::throw_on_error(Impl::GenericScan<Policy, F, Red>::run(policy, f, Red{f}, &total, nullptr));
+}
+template <class... P, class F, class VT, class = std::enable_if_t<is_view_v<VT>>, class = void>
+void parallel_scan(const std::string& /*label*/, const RangePolicy<P...>& policy, const F& f, const VT& total_view) {
+  using Policy = RangePolicy<P...>;
+  using V = typename VT::non_const_value_type;
+  using Red = Impl::FunctorReducer<F, V, typename Policy::work_tag>;
+  auto t = Impl::target_of_view(total_view);
+  Impl::throw_on_error(Impl::GenericScan<Policy, F, Red>::run(policy, f, Red{f}, t.host, t.dev));
+}
+// no total: the functor must publish its value_type (as in the reference, Kokkos_Parallel.hpp:348-367)
+template <class... P, class F>
+void parallel_scan(const std::string& /*label*/, const RangePolicy<P...>& policy, const F& f) {
+  using Policy = RangePolicy<P...>;
+  using V = typename Impl::scan_value_type_of<F>::type;
+  using Red = Impl::FunctorReducer<F, V, typename Policy::work_tag>;
+  Impl::throw_on_error(Impl::GenericScan<Policy, F, Red>::run(policy, f, Red{f}, (V*)nullptr, (V*)nullptr));
+}
+template <class... P, class F, class... R>
+void parallel_scan(const RangePolicy<P...>& policy, const F& f, R&&... r) { parallel_scan(std::string(), policy, f, static_cast<R&&>(r)...); }
+template <class F, class... R>
+void parallel_scan(const std::string& label, size_t n, const F& f, R&&... r) { parallel_scan(label, RangePolicy<>(0, (long long)n), f, static_cast<R&&>(r)...); }
+template <class F, class... R>
+void parallel_scan(size_t n, const F& f, R&&... r) { parallel_scan(std::string(), RangePolicy<>(0, (long long)n), f, static_cast<R&&>(r)...); }
+
+}  // namespace kb200
+#endif

@@ -1,0 +1,240 @@
+// kb200/Policy.hpp -- execution policies of the hot path, same names and template-property protocol as
+// core/src/Kokkos_ExecPolicy.hpp (RangePolicy :76-338, ChunkSize :45-53, TeamPolicy :614-725) and
+// core/src/KokkosExp_MDRangePolicy.hpp:169-427 (MDRangePolicy, Rank, Iterate), with the policy traits of
+// core/src/impl/Kokkos_AnalyzePolicy.hpp:165-190: execution space, Schedule<Static|Dynamic>, IndexType<T>,
+// LaunchBounds<maxT,minB> and a work tag may be given in any order.
+//
+// B200 specifics:
+//   * the default index type is 64-bit (the reference's Cuda default is `unsigned`, which is what made
+//     ranges > 2^31 a special case: CHANGELOG.md:70, TestReduce.hpp:650-675);
+//   * Schedule and ChunkSize are accepted and ignored, exactly as the reference's Cuda backend does
+//     (SURVEY.md section 8a, a23);
+//   * bound errors abort like the reference (Kokkos_ExecPolicy.hpp:235-251).
+#ifndef KB200_POLICY_HPP
+#define KB200_POLICY_HPP
+
+#include "B200.hpp"
+#include <array>
+#include <initializer_list>
+#include <type_traits>
+
+namespace kb200 {
+
+struct Static {};
+struct Dynamic {};
+template <class T> struct Schedule { using type = T; using schedule_type = Schedule; };
+template <class T> struct IndexType { using type = T; using index_type = IndexType; };
+template <unsigned MaxT = 0, unsigned MinB = 0>
+struct LaunchBounds { static constexpr unsigned maxTperB = MaxT, minBperSM = MinB; using launch_bounds = LaunchBounds; };
+struct ChunkSize { int value; explicit ChunkSize(int v) : value(v) {} };
+struct AUTO_t { constexpr const AUTO_t& operator()() const { return *this; } };
+constexpr AUTO_t AUTO{};
+
+enum class Iterate { Default, Left, Right };
+template <unsigned N, Iterate OuterDir = Iterate::Default, Iterate InnerDir = Iterate::Default>
+struct Rank { static constexpr int rank = (int)N; static constexpr Iterate outer_direction = OuterDir, inner_direction = InnerDir; };
+
+namespace Impl {
+template <class T> struct is_schedule : std::false_type {};
+template <class T> struct is_schedule<Schedule<T>> : std::true_type {};
+template <class T> struct is_index_type : std::false_type {};
+template <class T> struct is_index_type<IndexType<T>> : std::true_type {};
+template <class T> struct is_launch_bounds : std::false_type {};
+template <unsigned A, unsigned B> struct is_launch_bounds<LaunchBounds<A, B>> : std::true_type {};
+template <class T> struct is_rank : std::false_type {};
+template <unsigned N, Iterate A, Iterate B> struct is_rank<Rank<N, A, B>> : std::true_type {};
+template <class T> struct is_exec_space : std::is_same<T, B200> {};
+
+template <class... P> struct policy_traits;
+template <> struct policy_traits<> {
+  using schedule = Schedule<Static>; using index = void; using bounds = LaunchBounds<>; using tag = void; using rank = void;
+};
+template <class F, class... R>
+struct policy_traits<F, R...> {
+  using next = policy_traits<R...>;
+  static constexpr bool known = is_schedule<F>::value || is_index_type<F>::value || is_launch_bounds<F>::value ||
+                                is_rank<F>::value || is_exec_space<F>::value;
+  using schedule = std::conditional_t<is_schedule<F>::value, F, typename next::schedule>;
+  using index = std::conditional_t<is_index_type<F>::value, F, typename next::index>;
+  using bounds = std::conditional_t<is_launch_bounds<F>::value, F, typename next::bounds>;
+  using rank = std::conditional_t<is_rank<F>::value, F, typename next::rank>;
+  using tag = std::conditional_t<!known, F, typename next::tag>;  // anything unrecognised is the work tag
+};
+template <class IT> struct index_of { using type = typename IT::type; };
+template <> struct index_of<void> { using type = long long; };
+
+[[noreturn]] inline void policy_abort(const char* msg) {
+  std::fprintf(stderr, "%s\n", msg);
+  std::abort();
+}
+}  // namespace Impl
+
+// ------------------------------------------------------------------------------------------ RangePolicy
+template <class... Props>
+class RangePolicy {
+  using traits = Impl::policy_traits<Props...>;
+
+ public:
+  using execution_space = B200;
+  using execution_policy = RangePolicy;
+  using work_tag = typename traits::tag;
+  using schedule_type = typename traits::schedule;
+  using launch_bounds = typename traits::bounds;
+  using index_type = typename Impl::index_of<typename traits::index>::type;
+  using member_type = index_type;
+
+  RangePolicy() : m_begin(0), m_end(0) {}
+  RangePolicy(index_type b, index_type e) : m_begin(b), m_end(e) { check(); }
+  RangePolicy(const B200& s, index_type b, index_type e) : m_space(s), m_begin(b), m_end(e) { check(); }
+  RangePolicy(index_type b, index_type e, ChunkSize c) : m_begin(b), m_end(e), m_chunk(c.value) { check(); }
+  RangePolicy(const B200& s, index_type b, index_type e, ChunkSize c) : m_space(s), m_begin(b), m_end(e), m_chunk(c.value) { check(); }
+
+  const B200& space() const { return m_space; }
+  KB200_INLINE_FUNCTION index_type begin() const { return m_begin; }
+  KB200_INLINE_FUNCTION index_type end() const { return m_end; }
+  index_type chunk_size() const { return m_chunk; }
+  RangePolicy& set_chunk_size(int c) { m_chunk = c; return *this; }
+
+ private:
+  void check() {
+    if (m_end < m_begin) Impl::policy_abort("kb200::RangePolicy bounds error: The lower bound is greater than the upper bound");
+  }
+  B200 m_space;
+  index_type m_begin, m_end;
+  index_type m_chunk = 0;
+};
+
+// ------------------------------------------------------------------------------------------ MDRangePolicy
+template <class... Props>
+class MDRangePolicy {
+  using traits = Impl::policy_traits<Props...>;
+  static_assert(!std::is_void<typename traits::rank>::value, "kb200::MDRangePolicy needs a Rank<N> property");
+
+ public:
+  static constexpr int rank = traits::rank::rank;
+  static_assert(rank >= 2 && rank <= 6, "MDRangePolicy rank must be 2..6");
+  using execution_space = B200;
+  using execution_policy = MDRangePolicy;
+  using work_tag = typename traits::tag;
+  using launch_bounds = typename traits::bounds;
+  using index_type = typename Impl::index_of<typename traits::index>::type;
+  using point_type = std::array<index_type, rank>;
+  using tile_type = std::array<index_type, rank>;
+  // device iteration is Left/Left like the reference's Cuda backend (Cuda/Kokkos_Cuda_MDRangePolicy.hpp:25-35):
+  // dimension 0 is the fastest-varying one and maps to threadIdx.x
+  static constexpr Iterate outer_direction = Iterate::Left, inner_direction = Iterate::Left;
+
+  template <class L, class U>
+  MDRangePolicy(std::initializer_list<L> lower, std::initializer_list<U> upper) { init(lower, upper, std::initializer_list<index_type>{}); }
+  template <class L, class U, class Tl>
+  MDRangePolicy(std::initializer_list<L> lower, std::initializer_list<U> upper, std::initializer_list<Tl> tile) { init(lower, upper, tile); }
+  template <class L, class U>
+  MDRangePolicy(const B200& s, std::initializer_list<L> lower, std::initializer_list<U> upper) : m_space(s) { init(lower, upper, std::initializer_list<index_type>{}); }
+  template <class L, class U, class Tl>
+  MDRangePolicy(const B200& s, std::initializer_list<L> lower, std::initializer_list<U> upper, std::initializer_list<Tl> tile) : m_space(s) { init(lower, upper, tile); }
+  MDRangePolicy(const point_type& lower, const point_type& upper, const tile_type& tile = tile_type{}) { init_arrays(lower, upper, tile); }
+  MDRangePolicy(const B200& s, const point_type& lower, const point_type& upper, const tile_type& tile = tile_type{}) : m_space(s) { init_arrays(lower, upper, tile); }
+
+  const B200& space() const { return m_space; }
+  point_type m_lower{}, m_upper{};
+  tile_type m_tile{}, m_tile_end{};
+  index_type m_num_tiles = 0, m_prod_tile_dims = 1;
+  static constexpr int max_tile_product = 1024;  // one tile = one thread block
+
+ private:
+  template <class L, class U, class Tl>
+  void init(std::initializer_list<L> lo, std::initializer_list<U> up, std::initializer_list<Tl> tl) {
+    if ((int)lo.size() != rank || (int)up.size() != rank || ((int)tl.size() != rank && tl.size() != 0))
+      Impl::policy_abort("kb200::MDRangePolicy: Constructor initializer lists have wrong size");
+    point_type l{}, u{};
+    tile_type t{};
+    int k = 0; for (auto v : lo) l[k++] = (index_type)v;
+    k = 0; for (auto v : up) u[k++] = (index_type)v;
+    k = 0; for (auto v : tl) t[k++] = (index_type)v;
+    init_arrays(l, u, t);
+  }
+  void init_arrays(const point_type& l, const point_type& u, const tile_type& t) {
+    m_lower = l; m_upper = u; m_tile = t;
+    // defaults (B200): 32 threads along the contiguous dimension, then 4, 2, 1...: one warp = one 256-byte row
+    static constexpr int dflt[6] = {32, 4, 2, 1, 1, 1};
+    m_num_tiles = 1; m_prod_tile_dims = 1;
+    for (int d = 0; d < rank; ++d) {
+      if (m_upper[d] < m_lower[d]) Impl::policy_abort("kb200::MDRangePolicy bounds error: The lower bound is greater than its upper bound");
+      const index_type len = m_upper[d] - m_lower[d];
+      if (m_tile[d] <= 0) m_tile[d] = dflt[d];
+      if (m_tile[d] > len && len > 0) m_tile[d] = len;
+      if (m_tile[d] < 1) m_tile[d] = 1;
+      m_tile_end[d] = (len + m_tile[d] - 1) / m_tile[d];
+      m_num_tiles *= m_tile_end[d];
+      m_prod_tile_dims *= m_tile[d];
+    }
+    if (m_prod_tile_dims > max_tile_product) Impl::policy_abort("kb200::MDRangePolicy: tile dimensions exceed the maximum of 1024 threads per tile");
+  }
+  B200 m_space;
+};
+
+// ------------------------------------------------------------------------------------------ TeamPolicy
+struct PerTeamValue { size_t value; };
+struct PerThreadValue { size_t value; };
+inline PerTeamValue PerTeam(size_t v) { return PerTeamValue{v}; }
+inline PerThreadValue PerThread(size_t v) { return PerThreadValue{v}; }
+
+class B200TeamMember;
+
+template <class... Props>
+class TeamPolicy {
+  using traits = Impl::policy_traits<Props...>;
+
+ public:
+  using execution_space = B200;
+  using execution_policy = TeamPolicy;
+  using work_tag = typename traits::tag;
+  using launch_bounds = typename traits::bounds;
+  using index_type = typename Impl::index_of<typename traits::index>::type;
+  using member_type = B200TeamMember;
+
+  TeamPolicy() {}
+  TeamPolicy(int league, int team, int vec = 1) : m_league(league), m_team(team), m_vec(vec) { check(); }
+  TeamPolicy(int league, const AUTO_t&, int vec = 1) : m_league(league), m_team(-1), m_vec(vec) { check(); }
+  TeamPolicy(int league, const AUTO_t&, const AUTO_t&) : m_league(league), m_team(-1), m_vec(-1) { check(); }
+  TeamPolicy(int league, int team, const AUTO_t&) : m_league(league), m_team(team), m_vec(-1) { check(); }
+  TeamPolicy(const B200& s, int league, int team, int vec = 1) : m_space(s), m_league(league), m_team(team), m_vec(vec) { check(); }
+  TeamPolicy(const B200& s, int league, const AUTO_t&, int vec = 1) : m_space(s), m_league(league), m_team(-1), m_vec(vec) { check(); }
+
+  const B200& space() const { return m_space; }
+  int league_size() const { return m_league; }
+  int team_size() const { return m_team; }              // -1 = AUTO (resolved at launch)
+  int impl_vector_length() const { return m_vec; }      // -1 = AUTO
+  bool impl_auto_team_size() const { return m_team < 0; }
+  bool impl_auto_vector_length() const { return m_vec < 0; }
+  static int vector_length_max() { return 32; }         // Cuda_Parallel_Team.hpp:174
+  static int scratch_size_max(int level) { return level == 0 ? 200 * 1024 : (1 << 30); }
+  size_t scratch_size(int level, int team_size = -1) const {
+    const int ts = team_size > 0 ? team_size : (m_team > 0 ? m_team : 1);
+    return m_team_scratch[level] + m_thread_scratch[level] * (size_t)ts;
+  }
+  size_t team_scratch_size(int level) const { return m_team_scratch[level]; }
+  size_t thread_scratch_size(int level) const { return m_thread_scratch[level]; }
+  TeamPolicy& set_scratch_size(int level, PerTeamValue t) { chk_level(level); m_team_scratch[level] = t.value; return *this; }
+  TeamPolicy& set_scratch_size(int level, PerThreadValue t) { chk_level(level); m_thread_scratch[level] = t.value; return *this; }
+  TeamPolicy& set_scratch_size(int level, PerTeamValue a, PerThreadValue b) { chk_level(level); m_team_scratch[level] = a.value; m_thread_scratch[level] = b.value; return *this; }
+  TeamPolicy& set_scratch_size(int level, PerThreadValue b, PerTeamValue a) { return set_scratch_size(level, a, b); }
+  // team_size_max / team_size_recommended (Cuda_Parallel_Team.hpp:96-172): 1024-thread blocks, a multiple of a warp
+  template <class F, class Tag> int team_size_max(const F&, const Tag&) const { return 1024 / (m_vec > 0 ? m_vec : 1); }
+  template <class F, class Tag> int team_size_recommended(const F&, const Tag&) const { return impl_default_team_size(); }
+  int impl_default_team_size() const { const int v = m_vec > 0 ? m_vec : 1; return 256 / v > 0 ? 256 / v : 1; }
+
+ private:
+  void chk_level(int level) const { if (level < 0 || level > 1) Impl::policy_abort("kb200::TeamPolicy: scratch level must be 0 or 1"); }
+  void check() {
+    if (m_league < 0) Impl::policy_abort("kb200::TeamPolicy: negative league size");
+    if (m_vec > 32 || (m_vec > 0 && (m_vec & (m_vec - 1)))) Impl::policy_abort("kb200::TeamPolicy: vector length must be a power of two <= 32");
+    if (m_team > 0 && m_vec > 0 && m_team * m_vec > 1024) throw std::runtime_error("kb200::TeamPolicy: requested team_size * vector_length exceeds 1024 threads");
+  }
+  B200 m_space;
+  int m_league = 0, m_team = -1, m_vec = 1;
+  size_t m_team_scratch[2] = {0, 0}, m_thread_scratch[2] = {0, 0};
+};
+
+}  // namespace kb200
+#endif

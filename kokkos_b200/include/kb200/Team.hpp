@@ -1,0 +1,498 @@
+// kb200/Team.hpp -- hierarchical parallelism on the B200 execution space: TeamPolicy parallel_for /
+// parallel_reduce, the team handle, nested ranges, team/vector collectives, `single`, team scratch.
+//
+// Same vocabulary as the reference: member type (core/src/Cuda/Kokkos_Cuda_Team.hpp:72-349), nested
+// policies TeamThreadRange / TeamVectorRange / ThreadVectorRange, PerTeam / PerThread, nested
+// parallel_for / parallel_reduce / parallel_scan and single (Kokkos_Cuda_Team.hpp:368-1070),
+// ScratchMemorySpace with levels 0 (shared memory) and 1 (global arena) (core/src/Kokkos_ScratchSpace.hpp:37-170),
+// TeamPolicy launch (core/src/Cuda/Kokkos_Cuda_Parallel_Team.hpp:431-587,589-980).
+//
+// Mapping: block = (vector_length, team_size); a team "thread" is a group of vector_length lanes of one
+// warp; the league is walked by a persistent grid.  All collectives are register/shuffle based with one
+// shared-memory hop across warps (Collectives.hpp); the level-1 scratch is a per-block slice of an
+// instance-owned arena (no atomicCAS slot pool as in Cuda_Parallel_Team.hpp:392-429).
+#ifndef KB200_TEAM_HPP
+#define KB200_TEAM_HPP
+
+#include "Parallel.hpp"
+
+// Team-level functions are called from KB200_LAMBDA (= __host__ __device__) functors, so they must be
+// __host__ __device__ themselves; their bodies only exist in the device pass (KOKKOS_IF_ON_DEVICE in the reference).
+#ifdef __CUDA_ARCH__
+#define KB200_TEAM_DEVICE_ONLY(...) __VA_ARGS__
+#else
+#define KB200_TEAM_DEVICE_ONLY(...)
+#endif
+#define KB200_TEAM_FUNCTION __host__ __device__ __forceinline__
+
+namespace kb200 {
+namespace Impl {
+namespace tm {  // device builtins behind host-device wrappers (the host pass never executes them)
+KB200_TEAM_FUNCTION int tx() { KB200_TEAM_DEVICE_ONLY(return (int)threadIdx.x;) return 0; }
+KB200_TEAM_FUNCTION int ty() { KB200_TEAM_DEVICE_ONLY(return (int)threadIdx.y;) return 0; }
+KB200_TEAM_FUNCTION int nx() { KB200_TEAM_DEVICE_ONLY(return (int)blockDim.x;) return 1; }
+KB200_TEAM_FUNCTION int ny() { KB200_TEAM_DEVICE_ONLY(return (int)blockDim.y;) return 1; }
+KB200_TEAM_FUNCTION void sync() { KB200_TEAM_DEVICE_ONLY(__syncthreads();) }
+KB200_TEAM_FUNCTION void syncwarp();
+// lane mask of this thread's vector group: vector-level shuffles must name only the group, because the other
+// team threads sharing the warp may be in a different iteration (Cuda_Team.hpp does the same with blockDim.x masks)
+KB200_TEAM_FUNCTION unsigned vmask() {
+  KB200_TEAM_DEVICE_ONLY(
+    const int vl = (int)blockDim.x;
+    if (vl >= 32) return 0xffffffffu;
+    const int lane = (int)(threadIdx.x + blockDim.x * threadIdx.y) & 31;
+    return ((1u << vl) - 1u) << ((lane / vl) * vl);
+  )
+  return 0xffffffffu;
+}
+template <class T> KB200_TEAM_FUNCTION T up(const T& v, int d) { KB200_TEAM_DEVICE_ONLY(return shfl_up(v, (unsigned)d, vmask());) return v; }
+template <class T> KB200_TEAM_FUNCTION T down(const T& v, int d) { KB200_TEAM_DEVICE_ONLY(return shfl_down(v, (unsigned)d, vmask());) return v; }
+template <class T> KB200_TEAM_FUNCTION T idx(const T& v, int l) { KB200_TEAM_DEVICE_ONLY(return shfl_idx(v, l, vmask());) return v; }
+KB200_TEAM_FUNCTION void syncwarp() { KB200_TEAM_DEVICE_ONLY(__syncwarp(vmask());) }
+template <class Red> KB200_TEAM_FUNCTION void block_red(const Red& red, typename Red::value_type& v, void* smem) {
+  KB200_TEAM_DEVICE_ONLY(block_reduce(red, v, smem);)
+}
+template <class T> KB200_TEAM_FUNCTION T fetch_add(T* p, T v) {
+  KB200_TEAM_DEVICE_ONLY(
+    if constexpr (sizeof(T) == 8 && std::is_integral<T>::value) return (T)atomicAdd((unsigned long long*)p, (unsigned long long)v);
+    else return atomicAdd(p, v);
+  )
+  T o = *p; *p += v; return o;
+}
+}  // namespace tm
+}  // namespace Impl
+
+// ------------------------------------------------------------------------------------------ scratch space
+template <class ExecSpace>
+class ScratchMemorySpace {
+ public:
+  using is_scratch_tag = void;
+  using memory_space = ScratchMemorySpace;
+  using execution_space = ExecSpace;
+  static constexpr int ALIGN = 8;  // Kokkos_ScratchSpace.hpp:44
+
+  KB200_INLINE_FUNCTION ScratchMemorySpace() : m_iter{nullptr, nullptr}, m_end{nullptr, nullptr}, m_default_level(0) {}
+  KB200_INLINE_FUNCTION ScratchMemorySpace(void* p0, size_t s0, void* p1, size_t s1)
+      : m_iter{(char*)p0, (char*)p1}, m_end{(char*)p0 + s0, (char*)p1 + s1}, m_default_level(0) {}
+
+  template <class IntType>
+  KB200_INLINE_FUNCTION void* get_shmem(const IntType& size, int level = -1) const { return get_shmem_common(size, ALIGN, level); }
+  template <class IntType>
+  KB200_INLINE_FUNCTION void* get_shmem_aligned(const IntType& size, const ptrdiff_t alignment, int level = -1) const {
+    return get_shmem_common(size, alignment, level);
+  }
+  KB200_INLINE_FUNCTION ScratchMemorySpace set_level(int level) const { ScratchMemorySpace s(*this); s.m_default_level = level; return s; }
+
+ private:
+  template <class IntType>
+  KB200_INLINE_FUNCTION void* get_shmem_common(const IntType& size, const ptrdiff_t alignment, int level) const {
+    if (level == -1) level = m_default_level;
+    char*& it = m_iter[level];
+    const uintptr_t mis = reinterpret_cast<uintptr_t>(it) % alignment;
+    char* p = it + (mis ? alignment - mis : 0);
+    if (p + size > m_end[level]) return nullptr;  // out of scratch: nullptr, as the reference
+    it = p + size;
+    return p;
+  }
+  mutable char* m_iter[2];
+  char* m_end[2];
+  int m_default_level;
+};
+
+// ------------------------------------------------------------------------------------------ team handle
+class B200TeamMember {
+ public:
+  using execution_space = B200;
+  using scratch_memory_space = ScratchMemorySpace<B200>;
+
+  KB200_TEAM_FUNCTION B200TeamMember(void* collective_smem, void* l0, size_t l0_team, size_t l0_thread, void* l1, size_t l1_team,
+                                       size_t l1_thread, int league_rank, int league_size)
+      : m_collective(collective_smem), m_l0((char*)l0), m_l1((char*)l1), m_l0_team(l0_team), m_l0_thread(l0_thread),
+        m_l1_team(l1_team), m_l1_thread(l1_thread), m_league_rank(league_rank), m_league_size(league_size) {}
+
+  KB200_TEAM_FUNCTION int league_rank() const { return m_league_rank; }
+  KB200_TEAM_FUNCTION int league_size() const { return m_league_size; }
+  KB200_TEAM_FUNCTION int team_rank() const { return Impl::tm::ty(); }
+  KB200_TEAM_FUNCTION int team_size() const { return Impl::tm::ny(); }
+  KB200_TEAM_FUNCTION int impl_vector_lane() const { return Impl::tm::tx(); }
+  KB200_TEAM_FUNCTION int impl_vector_length() const { return Impl::tm::nx(); }
+  KB200_TEAM_FUNCTION void team_barrier() const { Impl::tm::sync(); }
+
+  // scratch handles (a fresh bump allocator per call, as in Cuda_Team.hpp:86-101)
+  KB200_TEAM_FUNCTION scratch_memory_space team_shmem() const { return team_scratch(0); }
+  KB200_TEAM_FUNCTION scratch_memory_space team_scratch(int level) const {
+    return scratch_memory_space(m_l0, m_l0_team, m_l1, m_l1_team).set_level(level);
+  }
+  KB200_TEAM_FUNCTION scratch_memory_space thread_scratch(int level) const {
+    return scratch_memory_space(m_l0 + m_l0_team + m_l0_thread * Impl::tm::ty(), m_l0_thread,
+                                m_l1 + m_l1_team + m_l1_thread * Impl::tm::ty(), m_l1_thread).set_level(level);
+  }
+
+  // ---- team collectives (all threads of the team must call) ----
+  template <class T>
+  KB200_TEAM_FUNCTION void team_broadcast(T& val, int thread_id) const {
+    T* s = reinterpret_cast<T*>(m_collective);
+    Impl::tm::sync();
+    if (Impl::tm::ty() == thread_id && Impl::tm::tx() == 0) *s = val;
+    Impl::tm::sync();
+    val = *s;
+    Impl::tm::sync();
+  }
+  template <class Closure, class T>
+  KB200_TEAM_FUNCTION void team_broadcast(const Closure& f, T& val, int thread_id) const {
+    f(val);
+    team_broadcast(val, thread_id);
+  }
+  // every thread ends with the team-wide result
+  template <class Red>
+  KB200_TEAM_FUNCTION void team_reduce(const Red& red, typename Red::value_type& value) const {
+    using V = typename Red::value_type;
+    V v = value;
+    if (Impl::tm::tx() != 0) red.init(v);  // a thread's value counts once, not once per vector lane
+    Impl::tm::sync();
+    Impl::tm::block_red(red, v, m_collective);
+    V* s = reinterpret_cast<V*>(m_collective);
+    Impl::tm::sync();
+    if (Impl::tm::tx() == 0 && Impl::tm::ty() == 0) *s = v;
+    Impl::tm::sync();
+    value = *s;
+    Impl::tm::sync();
+  }
+  template <class Red>
+  KB200_TEAM_FUNCTION void team_reduce(const Red& red) const {
+    typename Red::value_type v = red.reference();
+    team_reduce(red, v);
+    red.reference() = v;
+  }
+  // exclusive scan of `value` over team_rank; optional global accumulator gets the team total (Cuda_Team.hpp:249-256)
+  template <class T>
+  KB200_TEAM_FUNCTION T team_scan(const T& value, T* const global_accum = nullptr) const {
+    T* s = reinterpret_cast<T*>(m_collective);  // team_size + 1 entries fit: collective area is sized for 1024/vl + 2 values of 16 B
+    Impl::tm::sync();
+    if (Impl::tm::tx() == 0) s[Impl::tm::ty() + 1] = value;
+    if (Impl::tm::tx() == 0 && Impl::tm::ty() == 0) s[0] = T();
+    Impl::tm::sync();
+    if (Impl::tm::tx() == 0 && Impl::tm::ty() == 0) {
+      T run = T();
+      for (int k = 1; k <= Impl::tm::ny(); ++k) { const T c = s[k]; s[k] = run; run += c; }
+      T base = T();
+      if (global_accum) base = Impl::tm::fetch_add(global_accum, run);
+      s[0] = base;
+    }
+    Impl::tm::sync();
+    const T r = s[0] + s[Impl::tm::ty() + 1];
+    Impl::tm::sync();
+    return r;
+  }
+
+ private:
+  void* m_collective;
+  char *m_l0, *m_l1;
+  size_t m_l0_team, m_l0_thread, m_l1_team, m_l1_thread;
+  int m_league_rank, m_league_size;
+};
+
+// ------------------------------------------------------------------------------------------ nested policies
+namespace Impl {
+template <class I> struct TeamThreadRangeStruct { I begin, end; const B200TeamMember& member; };
+template <class I> struct ThreadVectorRangeStruct { I begin, end; const B200TeamMember& member; };
+template <class I> struct TeamVectorRangeStruct { I begin, end; const B200TeamMember& member; };
+struct ThreadSingleStruct { const B200TeamMember& member; };
+struct VectorSingleStruct { const B200TeamMember& member; };
+}  // namespace Impl
+
+template <class I>
+KB200_TEAM_FUNCTION Impl::TeamThreadRangeStruct<I> TeamThreadRange(const B200TeamMember& m, I count) { return {I(0), count, m}; }
+template <class I1, class I2>
+KB200_TEAM_FUNCTION Impl::TeamThreadRangeStruct<std::common_type_t<I1, I2>> TeamThreadRange(const B200TeamMember& m, I1 b, I2 e) {
+  using I = std::common_type_t<I1, I2>;
+  return {I(b), I(e), m};
+}
+template <class I>
+KB200_TEAM_FUNCTION Impl::ThreadVectorRangeStruct<I> ThreadVectorRange(const B200TeamMember& m, I count) { return {I(0), count, m}; }
+template <class I1, class I2>
+KB200_TEAM_FUNCTION Impl::ThreadVectorRangeStruct<std::common_type_t<I1, I2>> ThreadVectorRange(const B200TeamMember& m, I1 b, I2 e) {
+  using I = std::common_type_t<I1, I2>;
+  return {I(b), I(e), m};
+}
+template <class I>
+KB200_TEAM_FUNCTION Impl::TeamVectorRangeStruct<I> TeamVectorRange(const B200TeamMember& m, I count) { return {I(0), count, m}; }
+template <class I1, class I2>
+KB200_TEAM_FUNCTION Impl::TeamVectorRangeStruct<std::common_type_t<I1, I2>> TeamVectorRange(const B200TeamMember& m, I1 b, I2 e) {
+  using I = std::common_type_t<I1, I2>;
+  return {I(b), I(e), m};
+}
+KB200_TEAM_FUNCTION Impl::ThreadSingleStruct PerTeam(const B200TeamMember& m) { return {m}; }
+KB200_TEAM_FUNCTION Impl::VectorSingleStruct PerThread(const B200TeamMember& m) { return {m}; }
+
+// ---- nested parallel_for
+template <class I, class L>
+KB200_TEAM_FUNCTION void parallel_for(const Impl::TeamThreadRangeStruct<I>& r, const L& f) {
+  for (I i = r.begin + (I)Impl::tm::ty(); i < r.end; i += (I)Impl::tm::ny()) f(i);
+}
+template <class I, class L>
+KB200_TEAM_FUNCTION void parallel_for(const Impl::ThreadVectorRangeStruct<I>& r, const L& f) {
+  for (I i = r.begin + (I)Impl::tm::tx(); i < r.end; i += (I)Impl::tm::nx()) f(i);
+  Impl::tm::syncwarp();
+}
+template <class I, class L>
+KB200_TEAM_FUNCTION void parallel_for(const Impl::TeamVectorRangeStruct<I>& r, const L& f) {
+  for (I i = r.begin + (I)(Impl::tm::ty() * Impl::tm::nx() + Impl::tm::tx()); i < r.end; i += (I)(Impl::tm::ny() * Impl::tm::nx())) f(i);
+}
+
+namespace Impl {
+// reduce across the vector lanes of one thread (power-of-two groups inside a warp); every lane gets the result
+template <class Red>
+KB200_TEAM_FUNCTION void vector_reduce(const Red& red, typename Red::value_type& v) {
+  using V = typename Red::value_type;
+  // ordered fold inside the group: shfl_down tree, then broadcast from the group's first lane
+  const int vl = Impl::tm::nx();
+  const int lane = (Impl::tm::tx() + Impl::tm::nx() * Impl::tm::ty()) & 31;
+  for (int d = 1; d < vl; d <<= 1) {
+    V hi = tm::down(v, d);
+    if (Impl::tm::tx() + d < vl) red.join(v, hi);
+  }
+  v = tm::idx(v, lane - Impl::tm::tx());
+}
+template <class T> struct NestedSum {
+  using value_type = T;
+  KB200_TEAM_FUNCTION void init(T& v) const { v = T(); }
+  KB200_TEAM_FUNCTION void join(T& d, const T& s) const { d += s; }
+  KB200_TEAM_FUNCTION void final(T&) const {}
+};
+}  // namespace Impl
+
+// ---- nested parallel_reduce: result is a scalar (sum) or a reducer
+template <class I, class L, class R>
+KB200_TEAM_FUNCTION void parallel_reduce(const Impl::ThreadVectorRangeStruct<I>& r, const L& f, R&& result) {
+  using RD = std::decay_t<R>;
+  if constexpr (is_reducer_v<RD>) {
+    typename RD::value_type v;
+    result.init(v);
+    for (I i = r.begin + (I)Impl::tm::tx(); i < r.end; i += (I)Impl::tm::nx()) f(i, v);
+    Impl::vector_reduce(Impl::ReducerAdapter<RD>{result}, v);
+    result.reference() = v;
+  } else {
+    RD v = RD();
+    for (I i = r.begin + (I)Impl::tm::tx(); i < r.end; i += (I)Impl::tm::nx()) f(i, v);
+    Impl::vector_reduce(Impl::NestedSum<RD>{}, v);
+    result = v;
+  }
+}
+template <class I, class L, class R>
+KB200_TEAM_FUNCTION void parallel_reduce(const Impl::TeamThreadRangeStruct<I>& r, const L& f, R&& result) {
+  using RD = std::decay_t<R>;
+  if constexpr (is_reducer_v<RD>) {
+    typename RD::value_type v;
+    result.init(v);
+    for (I i = r.begin + (I)Impl::tm::ty(); i < r.end; i += (I)Impl::tm::ny()) f(i, v);
+    r.member.team_reduce(Impl::ReducerAdapter<RD>{result}, v);
+    result.reference() = v;
+  } else {
+    RD v = RD();
+    for (I i = r.begin + (I)Impl::tm::ty(); i < r.end; i += (I)Impl::tm::ny()) f(i, v);
+    r.member.team_reduce(Impl::NestedSum<RD>{}, v);
+    result = v;
+  }
+}
+template <class I, class L, class R>
+KB200_TEAM_FUNCTION void parallel_reduce(const Impl::TeamVectorRangeStruct<I>& r, const L& f, R&& result) {
+  using RD = std::decay_t<R>;
+  const I start = r.begin + (I)(Impl::tm::ty() * Impl::tm::nx() + Impl::tm::tx()), step = (I)(Impl::tm::ny() * Impl::tm::nx());
+  if constexpr (is_reducer_v<RD>) {
+    typename RD::value_type v;
+    result.init(v);
+    for (I i = start; i < r.end; i += step) f(i, v);
+    Impl::vector_reduce(Impl::ReducerAdapter<RD>{result}, v);
+    r.member.team_reduce(Impl::ReducerAdapter<RD>{result}, v);
+    result.reference() = v;
+  } else {
+    RD v = RD();
+    for (I i = start; i < r.end; i += step) f(i, v);
+    Impl::vector_reduce(Impl::NestedSum<RD>{}, v);
+    r.member.team_reduce(Impl::NestedSum<RD>{}, v);
+    result = v;
+  }
+}
+
+// ---- nested parallel_scan (sum semantics, f(i, partial, final)); ThreadVectorRange and TeamThreadRange
+template <class I, class L>
+KB200_TEAM_FUNCTION void parallel_scan(const Impl::ThreadVectorRangeStruct<I>& r, const L& f) {
+  using V = std::remove_reference_t<typename Impl::scan_arg_of<L, I>::type>;
+  const int vl = Impl::tm::nx();
+  const int lane = (Impl::tm::tx() + Impl::tm::nx() * Impl::tm::ty()) & 31;
+  V carry = V();
+  for (I base = r.begin; base < r.end; base += (I)vl) {
+    const I i = base + (I)Impl::tm::tx();
+    V c = V();
+    if (i < r.end) f(i, c, false);
+    V incl = c;  // inclusive scan over the group
+    for (int d = 1; d < vl; d <<= 1) {
+      V lo = Impl::tm::up(incl, d);
+      if (Impl::tm::tx() >= d) incl += lo;
+    }
+    V ex = carry + (incl - c);
+    if (i < r.end) f(i, ex, true);
+    carry += Impl::tm::idx(incl, lane - Impl::tm::tx() + vl - 1);
+  }
+}
+template <class I, class L>
+KB200_TEAM_FUNCTION void parallel_scan(const Impl::TeamThreadRangeStruct<I>& r, const L& f) {
+  using V = std::remove_reference_t<typename Impl::scan_arg_of<L, I>::type>;
+  V carry = V();
+  const I ts = (I)Impl::tm::ny();
+  for (I base = r.begin; base < r.end; base += ts) {  // uniform trip count: team_scan is a team collective
+    const I i = base + (I)Impl::tm::ty();
+    V c = V();
+    if (i < r.end) f(i, c, false);
+    V ex = carry + r.member.team_scan(c);
+    if (i < r.end) f(i, ex, true);
+    V tot = c;
+    r.member.team_reduce(Impl::NestedSum<V>{}, tot);
+    carry += tot;
+  }
+}
+
+// ---- single
+template <class L>
+KB200_TEAM_FUNCTION void single(const Impl::VectorSingleStruct&, const L& f) {
+  if (Impl::tm::tx() == 0) f();
+  Impl::tm::syncwarp();
+}
+template <class L>
+KB200_TEAM_FUNCTION void single(const Impl::ThreadSingleStruct&, const L& f) {
+  if (Impl::tm::tx() == 0 && Impl::tm::ty() == 0) f();
+}
+template <class L, class T>
+KB200_TEAM_FUNCTION void single(const Impl::VectorSingleStruct&, const L& f, T& val) {
+  const int lane = (Impl::tm::tx() + Impl::tm::nx() * Impl::tm::ty()) & 31;
+  if (Impl::tm::tx() == 0) f(val);
+  val = Impl::tm::idx(val, lane - Impl::tm::tx());
+}
+template <class L, class T>
+KB200_TEAM_FUNCTION void single(const Impl::ThreadSingleStruct& s, const L& f, T& val) {
+  if (Impl::tm::tx() == 0 && Impl::tm::ty() == 0) f(val);
+  s.member.team_broadcast(val, 0);
+}
+
+// ------------------------------------------------------------------------------------------ TeamPolicy launch
+namespace Impl {
+
+constexpr size_t kTeamCollectiveBytes = (1024 + 2) * 16;  // team_scan of <=1024 threads of <=16-byte values
+
+struct TeamLaunchParams {
+  int league_size;
+  size_t l0_team, l0_thread, l1_team, l1_thread;
+  char* l1_arena;       // grid * l1_per_team bytes
+  size_t l1_per_team;
+};
+
+template <class F, class Tag>
+__global__ void team_for_kernel(const __grid_constant__ F f, const TeamLaunchParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  for (int lr = blockIdx.x; lr < p.league_size; lr += gridDim.x) {
+    B200TeamMember m(smem, smem + kTeamCollectiveBytes, p.l0_team, p.l0_thread, p.l1_arena + (size_t)blockIdx.x * p.l1_per_team,
+                     p.l1_team, p.l1_thread, lr, p.league_size);
+    if constexpr (std::is_void<Tag>::value) f(m); else f(Tag{}, m);
+    if (lr + (int)gridDim.x < p.league_size) __syncthreads();  // scratch is reused by the next league member
+  }
+}
+
+template <class F, class Tag, class Red>
+__global__ void team_reduce_kernel(const __grid_constant__ F f, const __grid_constant__ Red red, const TeamLaunchParams p,
+                                   const ReduceScratch scratch) {
+  using V = typename Red::value_type;
+  extern __shared__ __align__(16) unsigned char smem[];
+  V acc;
+  red.init(acc);
+  for (int lr = blockIdx.x; lr < p.league_size; lr += gridDim.x) {
+    B200TeamMember m(smem, smem + kTeamCollectiveBytes, p.l0_team, p.l0_thread, p.l1_arena + (size_t)blockIdx.x * p.l1_per_team,
+                     p.l1_team, p.l1_thread, lr, p.league_size);
+    if constexpr (std::is_void<Tag>::value) f(m, acc); else f(Tag{}, m, acc);
+    if (lr + (int)gridDim.x < p.league_size) __syncthreads();
+  }
+  if (threadIdx.x != 0) red.init(acc);  // one contribution per team thread (Cuda_Parallel_Team.hpp:678-800)
+  __syncthreads();
+  block_reduce(red, acc, smem);
+  __syncthreads();
+  grid_reduce_and_store(red, acc, scratch, smem);
+}
+
+template <class Policy>
+struct TeamShape {
+  int team, vec, threads, grid;
+  size_t smem;
+  TeamLaunchParams p;
+  int setup(const Policy& pol, const void* kernel, size_t value_bytes) {
+    HostRuntime rt(pol.space().impl_instance());
+    vec = pol.impl_auto_vector_length() ? 1 : pol.impl_vector_length();
+    team = pol.impl_auto_team_size() ? (256 / vec > 0 ? 256 / vec : 1) : pol.team_size();
+    threads = team * vec;
+    if (threads > 1024) throw std::runtime_error("kb200::TeamPolicy: team_size * vector_length exceeds 1024");
+    p.league_size = pol.league_size();
+    p.l0_team = pol.team_scratch_size(0); p.l0_thread = pol.thread_scratch_size(0);
+    p.l1_team = pol.team_scratch_size(1); p.l1_thread = pol.thread_scratch_size(1);
+    const size_t l0 = p.l0_team + p.l0_thread * team;
+    size_t coll = kTeamCollectiveBytes;
+    if (value_bytes * 34 > coll) coll = value_bytes * 34;
+    smem = coll + l0 + 16;
+    if (smem > (size_t)220 * 1024)
+      throw std::runtime_error("kb200::TeamPolicy: requested too much level-0 scratch (shared memory) for this team size");
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int bps = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, threads, smem);
+    if (bps < 1) bps = 1;
+    const long long cap = (long long)rt.sm_count() * bps;
+    grid = (int)(p.league_size < cap ? (p.league_size > 0 ? p.league_size : 1) : cap);
+    p.l1_per_team = (p.l1_team + p.l1_thread * team + 255) & ~(size_t)255;
+    p.l1_arena = nullptr;
+    if (p.l1_per_team) {
+      void* arena = nullptr;
+      int rc = b200_scratch_get(pol.space().impl_instance(), B200_SCRATCH_TEAM_L1, p.l1_per_team * grid, &arena, nullptr);
+      if (rc) return rc;
+      p.l1_arena = (char*)arena;
+    }
+    return 0;
+  }
+};
+}  // namespace Impl
+
+template <class... P, class F>
+void parallel_for(const std::string& /*label*/, const TeamPolicy<P...>& pol, const F& f) {
+  using Tag = typename TeamPolicy<P...>::work_tag;
+  if (pol.league_size() <= 0) return;
+  auto k = Impl::team_for_kernel<F, Tag>;
+  Impl::TeamShape<TeamPolicy<P...>> sh;
+  Impl::throw_on_error(sh.setup(pol, (const void*)k, 16));
+  Impl::HostRuntime rt(pol.space().impl_instance());
+  k<<<sh.grid, dim3(sh.vec, sh.team, 1), sh.smem, rt.stream()>>>(f, sh.p);
+  Impl::throw_on_error(rt.check_launch("kb200::team_for_kernel"));
+}
+template <class... P, class F>
+void parallel_for(const TeamPolicy<P...>& pol, const F& f) { parallel_for(std::string(), pol, f); }
+
+namespace Impl {
+template <class... P, class F, class Red>
+void reduce_dispatch(const TeamPolicy<P...>& pol, const F& f, const Red& red, ResultTarget<typename Red::value_type> t) {
+  using Tag = typename TeamPolicy<P...>::work_tag;
+  using V = typename Red::value_type;
+  auto k = team_reduce_kernel<F, Tag, Red>;
+  TeamShape<TeamPolicy<P...>> sh;
+  throw_on_error(sh.setup(pol, (const void*)k, sizeof(V)));
+  HostRuntime rt(pol.space().impl_instance());
+  ReduceScratch s;
+  void *slot_dev = nullptr, *slot_host = nullptr;
+  throw_on_error(rt.reduce_scratch((size_t)sh.grid * sizeof(V), sizeof(V), t.host != nullptr, &s.partials, &s.ticket, &slot_dev, &slot_host));
+  s.result0 = t.host ? slot_dev : (void*)t.dev;
+  s.result1 = t.host ? (void*)t.dev : nullptr;
+  k<<<sh.grid, dim3(sh.vec, sh.team, 1), sh.smem, rt.stream()>>>(f, red, sh.p, s);
+  throw_on_error(rt.check_launch("kb200::team_reduce_kernel"));
+  if (t.host) {
+    throw_on_error(rt.fence("kb200::parallel_reduce(TeamPolicy): fence to hand the scalar result to the host"));
+    memcpy(t.host, slot_host, sizeof(V));
+  }
+}
+}  // namespace Impl
+
+}  // namespace kb200
+#endif

@@ -67,7 +67,8 @@ struct view_props<First, Rest...> {
   using next = view_props<Rest...>;
   static constexpr bool is_layout = std::is_same<First, LayoutLeft>::value || std::is_same<First, LayoutRight>::value;
   static constexpr bool is_space = std::is_same<First, HostSpace>::value || std::is_same<First, B200Space>::value ||
-                                   std::is_same<First, B200HostPinnedSpace>::value || std::is_same<First, B200>::value;
+                                   std::is_same<First, B200HostPinnedSpace>::value || std::is_same<First, B200>::value ||
+                                   std::is_same<First, ScratchMemorySpace<B200>>::value;
   using layout = std::conditional_t<is_layout, First, typename next::layout>;
   using space_raw = std::conditional_t<is_space, First, typename next::space>;
   using space = std::conditional_t<std::is_same<space_raw, B200>::value, B200Space, space_raw>;
@@ -130,6 +131,16 @@ class View {
     set_extents(n0, n1, n2);
   }
 
+  // View over team/thread scratch memory: View<T*, ScratchSpace, Unmanaged>(team.team_scratch(level), n)
+  template <class S, class = typename S::is_scratch_tag>
+  KB200_INLINE_FUNCTION View(const S& scratch, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0) : m_rec(nullptr) {
+    set_extents(n0, n1, n2);
+    m_data = static_cast<pointer_type>(scratch.get_shmem_aligned(size() * sizeof(value_type), alignof(value_type) > 8 ? alignof(value_type) : 8));
+  }
+  static constexpr size_t shmem_size(size_t n0 = 0, size_t n1 = 0, size_t n2 = 0) {
+    return (rank > 0 ? n0 : 1) * (rank > 1 ? n1 : 1) * (rank > 2 ? n2 : 1) * sizeof(value_type) + 8;
+  }
+
   KB200_INLINE_FUNCTION View(const View& o) : m_data(o.m_data), m_rec(o.m_rec) { copy_ext(o); retain(); }
   KB200_INLINE_FUNCTION View(View&& o) noexcept : m_data(o.m_data), m_rec(o.m_rec) { copy_ext(o); o.m_rec = nullptr; o.m_data = nullptr; }
   // const-adding / trait-changing conversions between compatible Views
@@ -185,6 +196,7 @@ class View {
   std::string label() const { return m_rec ? m_rec->label : std::string(); }
   int use_count() const { return m_rec ? m_rec->refcount : 0; }
   KB200_INLINE_FUNCTION Impl::AllocRecord* impl_record() const { return m_rec; }
+  void impl_window(size_t offset, size_t count) { m_data += offset; m_ext[0] = count; }
 
  private:
   KB200_INLINE_FUNCTION void set_extents(size_t n0, size_t n1, size_t n2) {
@@ -245,25 +257,15 @@ template <class D, class... P> struct is_view<View<D, P...>> : std::true_type {}
 template <class T> constexpr bool is_view_v = is_view<std::decay_t<T>>::value;
 
 // ---------------------------------------------------------------- subview (rank-1 ranges)
+// shares ownership with the parent (the reference's subviews share the allocation record)
 template <class D, class... P, class I0, class I1>
 View<D, P...> subview(const View<D, P...>& v, const std::pair<I0, I1>& r) {
   static_assert(View<D, P...>::rank == 1, "kb200::subview: rank-1 Views only");
   if ((size_t)r.second > v.extent(0) || (size_t)r.first > (size_t)r.second) throw std::runtime_error("kb200::subview: range out of bounds");
-  View<D, P...> s(v);  // shares ownership
-  struct Access : View<D, P...> {};  // keep the allocation alive, re-point the window
-  View<D, P...> w(v.data() + r.first, (size_t)(r.second - r.first));
-  // an unmanaged window plus a keep-alive copy would double the handle; the window alone is enough when the parent
-  // outlives it (the reference's subviews share the record: emulate by copying the record pointer)
-  return Impl_subview_attach(w, s);
+  View<D, P...> s(v);
+  s.impl_window((size_t)r.first, (size_t)(r.second - r.first));
+  return s;
 }
-template <class V>
-V Impl_subview_attach(V& window, const V& owner) {
-  V out(owner);                      // retains the record
-  std::memcpy((void*)&out, (void*)&window, offsetof_data_ext<V>());  // overwrite pointer + extents, keep record
-  return out;
-}
-template <class V>
-constexpr size_t offsetof_data_ext() { return sizeof(void*) + 3 * sizeof(size_t); }
 
 // ---------------------------------------------------------------- deep_copy
 namespace Impl {

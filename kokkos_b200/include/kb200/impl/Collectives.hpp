@@ -40,16 +40,16 @@ KB200_DEVICE_FUNCTION T shfl_words(const T& v, ShflOp op) {
   return r;
 }
 template <class T>
-KB200_DEVICE_FUNCTION T shfl_down(const T& v, unsigned delta) {
-  return shfl_words(v, [=](unsigned x) { return __shfl_down_sync(kFullMask, x, delta); });
+KB200_DEVICE_FUNCTION T shfl_down(const T& v, unsigned delta, unsigned mask = kFullMask) {
+  return shfl_words(v, [=](unsigned x) { return __shfl_down_sync(mask, x, delta); });
 }
 template <class T>
-KB200_DEVICE_FUNCTION T shfl_up(const T& v, unsigned delta) {
-  return shfl_words(v, [=](unsigned x) { return __shfl_up_sync(kFullMask, x, delta); });
+KB200_DEVICE_FUNCTION T shfl_up(const T& v, unsigned delta, unsigned mask = kFullMask) {
+  return shfl_words(v, [=](unsigned x) { return __shfl_up_sync(mask, x, delta); });
 }
 template <class T>
-KB200_DEVICE_FUNCTION T shfl_idx(const T& v, int lane) {
-  return shfl_words(v, [=](unsigned x) { return __shfl_sync(kFullMask, x, lane); });
+KB200_DEVICE_FUNCTION T shfl_idx(const T& v, int lane, unsigned mask = kFullMask) {
+  return shfl_words(v, [=](unsigned x) { return __shfl_sync(mask, x, lane); });
 }
 template <class T>
 KB200_DEVICE_FUNCTION T shfl_xor(const T& v, int m) {
@@ -66,24 +66,27 @@ struct redux_op_of { static constexpr int value = ReduxNone; };
 template <class Red>
 struct redux_op_of<Red, std::void_t<decltype(Red::redux_op)>> { static constexpr int value = Red::redux_op; };
 
+// `nl` = number of live lanes of this warp (32 except in the last warp of a block whose size is not a multiple of 32)
 template <class Red>
-KB200_DEVICE_FUNCTION void warp_reduce(const Red& red, typename Red::value_type& v) {
+KB200_DEVICE_FUNCTION void warp_reduce(const Red& red, typename Red::value_type& v, int nl = kWarp) {
   using V = typename Red::value_type;
   constexpr int op = redux_op_of<Red>::value;
+  const unsigned mask = nl >= kWarp ? kFullMask : ((1u << nl) - 1u);
   if constexpr (op != ReduxNone && std::is_integral<V>::value && sizeof(V) == 4) {
     // redux.sync: one instruction instead of 5 shuffle+op rounds (SASS: REDUX)
-    if constexpr (op == ReduxAdd) v = (V)__reduce_add_sync(kFullMask, v);
-    if constexpr (op == ReduxMin) v = (V)__reduce_min_sync(kFullMask, v);
-    if constexpr (op == ReduxMax) v = (V)__reduce_max_sync(kFullMask, v);
-    if constexpr (op == ReduxAnd) v = (V)__reduce_and_sync(kFullMask, (unsigned)v);
-    if constexpr (op == ReduxOr) v = (V)__reduce_or_sync(kFullMask, (unsigned)v);
+    if constexpr (op == ReduxAdd) v = (V)__reduce_add_sync(mask, v);
+    if constexpr (op == ReduxMin) v = (V)__reduce_min_sync(mask, v);
+    if constexpr (op == ReduxMax) v = (V)__reduce_max_sync(mask, v);
+    if constexpr (op == ReduxAnd) v = (V)__reduce_and_sync(mask, (unsigned)v);
+    if constexpr (op == ReduxOr) v = (V)__reduce_or_sync(mask, (unsigned)v);
   } else {
+    const int lane = (threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) & 31;
 #pragma unroll
     for (int d = 1; d < kWarp; d <<= 1) {
-      V hi = shfl_down(v, d);  // value of lane+d: the HIGHER-ranked operand
-      // lanes whose partner is out of range receive their own value back; their result is
-      // never consumed by lane 0's fold, so the extra join is harmless.
-      red.join(v, hi);
+      V hi = shfl_down(v, d, mask);  // value of lane+d: the HIGHER-ranked operand
+      // a partner beyond the live lanes contributes nothing; within a full warp an out-of-range partner
+      // returns the lane's own value, whose result lane 0's fold never consumes
+      if (nl >= kWarp || lane + d < nl) red.join(v, hi);
     }
   }
 }
@@ -97,7 +100,8 @@ KB200_DEVICE_FUNCTION void block_reduce(const Red& red, typename Red::value_type
   const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
   const int nthreads = blockDim.x * blockDim.y * blockDim.z;
   const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
-  warp_reduce(red, v);
+  const int live = nthreads - (warp << 5);
+  warp_reduce(red, v, live < kWarp ? live : kWarp);
   if (nwarps == 1) return;
   if (lane == 0) s[warp] = v;
   __syncthreads();

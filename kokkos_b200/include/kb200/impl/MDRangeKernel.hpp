@@ -1,0 +1,181 @@
+// kb200/impl/MDRangeKernel.hpp -- MDRangePolicy<Rank<2..6>> parallel_for / parallel_reduce.
+//
+// Replaces ParallelFor/ParallelReduce<...,MDRangePolicy,Cuda> (core/src/Cuda/Kokkos_Cuda_Parallel_MDRange.hpp:
+// 69-246,248-497) and the DeviceIterateTile maps (core/src/impl/KokkosExp_IterateTileGPU.hpp:71-1156,1206-1305).
+//
+// Mapping: a tile is a thread block whose SHAPE is the tile (blockDim.x = tile[0] along the contiguous
+// dimension, blockDim.y = tile[1], blockDim.z = product of the remaining tile extents), so the hardware's
+// threadIdx supplies the in-tile coordinates and no division is executed per element.  A persistent grid
+// (SMs x resident blocks) strides over the tiles; the tile coordinates advance by a pre-decomposed stride
+// with carries (adds and compares only).  The reference's reduce variant instead launches <= 512 blocks
+// with tile_prod of 256 threads active and pays a div/mod per rank per element.
+// Reductions reuse the block/grid combine of Collectives.hpp (ordered, ticketed, result to a pinned slot).
+#ifndef KB200_IMPL_MDRANGEKERNEL_HPP
+#define KB200_IMPL_MDRANGEKERNEL_HPP
+
+#include "Collectives.hpp"
+#include "HostRuntime.hpp"
+#include <utility>
+
+namespace kb200 {
+namespace Impl {
+
+template <int RANK, class Index>
+struct MDParams {
+  Index lower[RANK], upper[RANK], tile[RANK], tile_end[RANK];
+  Index stride[RANK];  // gridDim.x decomposed in the mixed radix tile_end[] (dimension 0 fastest)
+  long long num_tiles;
+};
+
+template <class Tag, class F, class Index, size_t... Is, class... Extra>
+KB200_DEVICE_FUNCTION void md_invoke(const F& f, const Index* idx, std::index_sequence<Is...>, Extra&... extra) {
+  if constexpr (std::is_void<Tag>::value) f(idx[Is]..., extra...);
+  else f(Tag{}, idx[Is]..., extra...);
+}
+
+// walks the tiles owned by this block; calls op(idx) for every in-range point handled by this thread
+template <int RANK, class Index, class Op>
+KB200_DEVICE_FUNCTION void md_walk(const MDParams<RANK, Index>& p, Op op) {
+  // this thread's fixed offset inside any tile
+  Index off[RANK];
+  off[0] = (Index)threadIdx.x;
+  off[1] = (Index)threadIdx.y;
+  {
+    Index zz = (Index)threadIdx.z;
+#pragma unroll
+    for (int d = 2; d < RANK; ++d) { off[d] = zz % p.tile[d]; zz /= p.tile[d]; }
+  }
+  // tile coordinates of the first tile of this block (one decomposition per block, not per element)
+  Index t[RANK];
+  {
+    long long rem = blockIdx.x;
+#pragma unroll
+    for (int d = 0; d < RANK; ++d) { t[d] = (Index)(rem % p.tile_end[d]); rem /= p.tile_end[d]; }
+  }
+  for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    Index idx[RANK];
+    bool in = true;
+#pragma unroll
+    for (int d = 0; d < RANK; ++d) {
+      idx[d] = p.lower[d] + t[d] * p.tile[d] + off[d];
+      in = in && (idx[d] < p.upper[d]);
+    }
+    if (in) op(idx);
+    // advance by the grid stride: mixed-radix add with carry
+    Index carry = 0;
+#pragma unroll
+    for (int d = 0; d < RANK; ++d) {
+      t[d] += p.stride[d] + carry;
+      carry = 0;
+      if (t[d] >= p.tile_end[d]) { t[d] -= p.tile_end[d]; carry = 1; }
+    }
+  }
+}
+
+template <class F, class Tag, int RANK, class Index>
+__global__ void mdrange_for_kernel(const __grid_constant__ F f, const __grid_constant__ MDParams<RANK, Index> p) {
+  md_walk<RANK, Index>(p, [&](const Index* idx) { md_invoke<Tag>(f, idx, std::make_index_sequence<RANK>{}); });
+}
+
+template <class F, class Tag, class Red, int RANK, class Index>
+__global__ void mdrange_reduce_kernel(const __grid_constant__ F f, const __grid_constant__ Red red,
+                                      const __grid_constant__ MDParams<RANK, Index> p, const ReduceScratch scratch) {
+  using V = typename Red::value_type;
+  __shared__ __align__(16) unsigned char smem[32 * sizeof(V)];
+  V acc;
+  red.init(acc);
+  md_walk<RANK, Index>(p, [&](const Index* idx) { md_invoke<Tag>(f, idx, std::make_index_sequence<RANK>{}, acc); });
+  block_reduce(red, acc, smem);
+  __syncthreads();
+  grid_reduce_and_store(red, acc, scratch, smem);
+}
+
+template <class Policy>
+struct MDLaunchShape {
+  static constexpr int RANK = Policy::rank;
+  using Index = typename Policy::index_type;
+  MDParams<RANK, Index> p;
+  dim3 block;
+  int threads;
+  explicit MDLaunchShape(const Policy& pol) {
+    long long z = 1;
+    for (int d = 0; d < RANK; ++d) {
+      p.lower[d] = pol.m_lower[d]; p.upper[d] = pol.m_upper[d]; p.tile[d] = pol.m_tile[d]; p.tile_end[d] = pol.m_tile_end[d];
+      if (d >= 2) z *= pol.m_tile[d];
+    }
+    p.num_tiles = (long long)pol.m_num_tiles;
+    block = dim3((unsigned)pol.m_tile[0], (unsigned)pol.m_tile[1], (unsigned)z);
+    threads = (int)(block.x * block.y * block.z);
+    if (block.z > 64) throw std::runtime_error("kb200::MDRangePolicy: product of tile extents beyond dimension 1 exceeds 64 (blockDim.z limit)");
+  }
+  void set_grid(int grid) {
+    long long rem = grid;
+    for (int d = 0; d < RANK; ++d) {
+      const long long e = p.tile_end[d] > 0 ? (long long)p.tile_end[d] : 1;
+      p.stride[d] = (Index)(rem % e);
+      rem /= e;
+    }
+  }
+};
+
+template <class Policy, class F>
+struct MDRangeFor {
+  static int run(const Policy& pol, const F& f) {
+    if (pol.m_num_tiles <= 0) return 0;
+    constexpr int RANK = Policy::rank;
+    using Index = typename Policy::index_type;
+    using Tag = typename Policy::work_tag;
+    MDLaunchShape<Policy> sh(pol);
+    HostRuntime rt(pol.space().impl_instance());
+    auto k = mdrange_for_kernel<F, Tag, RANK, Index>;
+    int bps = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, sh.threads, 0);
+    if (bps < 1) bps = 1;
+    const long long cap = (long long)rt.sm_count() * bps * 4;  // a few waves: tiles are short
+    const int grid = (int)(sh.p.num_tiles < cap ? sh.p.num_tiles : cap);
+    sh.set_grid(grid);
+    k<<<grid, sh.block, 0, rt.stream()>>>(f, sh.p);
+    return rt.check_launch("kb200::mdrange_for_kernel");
+  }
+};
+
+template <class Policy, class F, class Red>
+struct MDRangeReduce {
+  using V = typename Red::value_type;
+  static int run(const Policy& pol, const F& f, const Red& red, V* result_host, V* result_dev) {
+    constexpr int RANK = Policy::rank;
+    using Index = typename Policy::index_type;
+    using Tag = typename Policy::work_tag;
+    MDLaunchShape<Policy> sh(pol);
+    HostRuntime rt(pol.space().impl_instance());
+    auto k = mdrange_reduce_kernel<F, Tag, Red, RANK, Index>;
+    int bps = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, sh.threads, 0);
+    if (bps < 1) bps = 1;
+    const long long cap = (long long)rt.sm_count() * bps;
+    long long tiles = sh.p.num_tiles;
+    const int grid = (int)(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
+    sh.set_grid(grid);
+    if (tiles < 1) {  // zero-length range: the result is the identity (TestMDRangeReduce.hpp:48-63)
+      sh.p.num_tiles = 0;
+      sh.block = dim3(32, 1, 1);
+    }
+    ReduceScratch s;
+    void *slot_dev = nullptr, *slot_host = nullptr;
+    int rc;
+    if ((rc = rt.reduce_scratch((size_t)grid * sizeof(V), sizeof(V), result_host != nullptr, &s.partials, &s.ticket, &slot_dev, &slot_host))) return rc;
+    s.result0 = result_host ? slot_dev : (void*)result_dev;
+    s.result1 = result_host ? (void*)result_dev : nullptr;
+    k<<<grid, sh.block, 0, rt.stream()>>>(f, red, sh.p, s);
+    if ((rc = rt.check_launch("kb200::mdrange_reduce_kernel"))) return rc;
+    if (result_host) {
+      if ((rc = rt.fence("kb200::parallel_reduce(MDRange): fence to hand the scalar result to the host"))) return rc;
+      memcpy(result_host, slot_host, sizeof(V));
+    }
+    return 0;
+  }
+};
+
+}  // namespace Impl
+}  // namespace kb200
+#endif

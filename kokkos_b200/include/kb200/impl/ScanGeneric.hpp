@@ -1,0 +1,282 @@
+// kb200/impl/ScanGeneric.hpp -- parallel_scan over RangePolicy for an arbitrary Kokkos scan functor
+// f(i, update, final) and an arbitrary static value_type with an associative (not necessarily commutative) join.
+//
+// Replaces ParallelScan / ParallelScanWithTotal<...,RangePolicy,Cuda>
+// (core/src/Cuda/Kokkos_Cuda_Parallel_Range.hpp:390-701,704-1047): two launches, the functor called three
+// times per index, a block-wide shared-memory scan every 128 elements.
+//
+// One launch, functor called exactly TWICE per index (as on the OpenMP oracle):
+//   pass 1  striped/coalesced: element e = j*BLOCK + tid ; c = identity ; f(i, c, false) -> contribution c
+//           -> shared memory;
+//   blocked each thread folds ITEMS consecutive contributions (ITEMS odd: conflict-free smem), ordered
+//           warp scan of the thread totals (shuffles), one cross-warp hop;
+//   chain   tile aggregate published, decoupled look-back over the predecessors (ordered fold, so
+//           non-commutative joins see operands in index order), inclusive prefix published;
+//   pass 2  exclusive prefixes written back to shared memory (blocked), read striped:
+//           u = prefix ; f(i, u, true).
+// Descriptors: status word (epoch<<2|state, st.release / ld.acquire) + two value slots per tile.
+#ifndef KB200_IMPL_SCANGENERIC_HPP
+#define KB200_IMPL_SCANGENERIC_HPP
+
+#include "Collectives.hpp"
+#include "HostRuntime.hpp"
+#include "Ptx.hpp"
+#include "ScanContig.hpp"
+
+namespace kb200 {
+namespace Impl {
+
+template <class V>
+struct GenericScanScratch {
+  unsigned long long* status;  // [ntiles]
+  V* agg;                      // [ntiles]
+  V* incl;                     // [ntiles]
+  unsigned long long epoch;
+  unsigned long long* counter;
+  unsigned long long counter_base;
+};
+
+template <class V>
+KB200_DEVICE_FUNCTION void store_value(V* dst, const V& v) { *dst = v; }
+
+// ordered inclusive warp scan: lane l ends with x0 (+) ... (+) xl
+template <class Red>
+KB200_DEVICE_FUNCTION void warp_incl_scan_ordered(const Red& red, typename Red::value_type& v, int lane) {
+  using V = typename Red::value_type;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    V lo = shfl_up(v, d);
+    if (lane >= d) { red.join(lo, v); v = lo; }
+  }
+}
+
+// exclusive prefix of tile `tile` (>0), folded in tile order.  Warp-collective; result valid in every lane.
+template <class Red>
+KB200_DEVICE_FUNCTION typename Red::value_type lookback_ordered(const Red& red, const GenericScanScratch<typename Red::value_type>& s,
+                                                                int64 tile, int lane) {
+  using V = typename Red::value_type;
+  V excl;
+  red.init(excl);
+  bool have = false;
+  int64 wbase = tile - 1;
+  while (true) {
+    const int64 idx = wbase - lane;
+    V val;
+    red.init(val);
+    int state;  // 1 = aggregate, 2 = inclusive prefix, 0 = not yet published
+    if (idx >= 0) {
+      const unsigned long long st = ptx::ld_acquire_u64(s.status + idx);
+      state = ((st >> 2) == s.epoch) ? (int)(st & 3ull) : 0;
+      if (state == 1) val = load_cg(s.agg + idx);
+      if (state == 2) val = load_cg(s.incl + idx);
+    } else {
+      state = 2;  // before the first tile: the identity is an inclusive prefix
+    }
+    const unsigned term = __ballot_sync(kFullMask, state == 2);
+    const unsigned inval = __ballot_sync(kFullMask, state == 0);
+    const int first_term = term ? (__ffs(term) - 1) : 32;
+    const unsigned needed = first_term >= 31 ? kFullMask : ((2u << first_term) - 1u);
+    if (inval & needed) { __nanosleep(100); continue; }
+    if (lane > first_term) red.init(val);  // older than the nearest resolved tile: not needed
+    // fold lanes first_term .. 0 (older tile = higher lane = LEFT operand)
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      V hi = shfl_down(val, d);
+      if (lane + d < 32) { red.join(hi, val); val = hi; }
+    }
+    V window = shfl_idx(val, 0);
+    if (have) { red.join(window, excl); }
+    excl = window;
+    have = true;
+    if (term) return excl;
+    wbase -= 32;
+  }
+}
+
+template <class F, class Tag, class Index, class Red, int BLOCK, int ITEMS>
+__global__ void __launch_bounds__(BLOCK)
+    generic_scan_kernel(const __grid_constant__ F f, const __grid_constant__ Red red, const Index begin, const int64 n,
+                        const int64 ntiles, const GenericScanScratch<typename Red::value_type> s,
+                        typename Red::value_type* total0, typename Red::value_type* total1) {
+  using V = typename Red::value_type;
+  constexpr int TILE = BLOCK * ITEMS;
+  constexpr int NWARPS = BLOCK / 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  V* const vals = reinterpret_cast<V*>(smem_raw);                       // TILE values
+  V* const s_warp = vals + TILE;                                         // 32 values
+  V* const s_prefix = s_warp + 32;                                       // 1 value
+  __shared__ int64 s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  while (true) {
+    if (tid == 0) s_tile = (int64)(atomicAdd(s.counter, 1ull) - s.counter_base);
+    __syncthreads();
+    const int64 tile = s_tile;
+    if (tile >= ntiles) break;
+    const int64 tbase = tile * TILE;
+
+    // ---- pass 1: contributions, coalesced
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const int e = j * BLOCK + tid;
+      const int64 i = tbase + e;
+      V c;
+      red.init(c);
+      if (i < n) {
+        if constexpr (std::is_void<Tag>::value) f((Index)(begin + (Index)i), c, false);
+        else f(Tag{}, (Index)(begin + (Index)i), c, false);
+      }
+      vals[e] = c;
+    }
+    __syncthreads();
+
+    // ---- blocked fold of ITEMS consecutive contributions
+    V loc[ITEMS];
+    V tsum;
+    red.init(tsum);
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      loc[k] = vals[tid * ITEMS + k];
+      red.join(tsum, loc[k]);
+    }
+    V tincl = tsum;
+    warp_incl_scan_ordered(red, tincl, lane);
+    if (lane == 31) s_warp[warp] = tincl;
+    __syncthreads();
+    if (warp == 0) {
+      V w;
+      red.init(w);
+      if (lane < NWARPS) w = s_warp[lane];
+      V wi = w;
+      warp_incl_scan_ordered(red, wi, lane);
+      V wex = shfl_up(wi, 1);  // exclusive warp prefix
+      if (lane == 0) red.init(wex);
+      if (lane < NWARPS) s_warp[lane] = wex;
+      V agg = shfl_idx(wi, NWARPS - 1);
+      V excl;
+      red.init(excl);
+      if (tile == 0) {
+        if (lane == 0) {
+          store_value(s.incl + tile, agg);
+          ptx::st_release_u64(s.status + tile, (s.epoch << 2) | 2ull);
+        }
+      } else {
+        if (lane == 0) {
+          store_value(s.agg + tile, agg);
+          ptx::st_release_u64(s.status + tile, (s.epoch << 2) | 1ull);
+        }
+        excl = lookback_ordered(red, s, tile, lane);
+        if (lane == 0) {
+          V inc = excl;
+          red.join(inc, agg);
+          store_value(s.incl + tile, inc);
+          ptx::st_release_u64(s.status + tile, (s.epoch << 2) | 2ull);
+        }
+      }
+      if (lane == 0) {
+        *s_prefix = excl;
+        if (tile == ntiles - 1 && (total0 || total1)) {
+          V total = excl;
+          red.join(total, agg);
+          // parallel_scan's total is the plain running value (no final(): Kokkos_Parallel.hpp:405-425)
+          if (total0) *total0 = total;
+          if (total1) *total1 = total;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- exclusive prefix of every element, blocked write-back
+    {
+      V run = *s_prefix;                 // tile prefix
+      { V wp = s_warp[warp]; red.join(run, wp); }
+      V tex = shfl_up(tincl, 1);         // exclusive thread prefix inside the warp
+      if (lane != 0) red.join(run, tex);
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {
+        vals[tid * ITEMS + k] = run;
+        red.join(run, loc[k]);
+      }
+    }
+    __syncthreads();
+
+    // ---- pass 2: final call, coalesced
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const int e = j * BLOCK + tid;
+      const int64 i = tbase + e;
+      if (i < n) {
+        V u = vals[e];
+        if constexpr (std::is_void<Tag>::value) f((Index)(begin + (Index)i), u, true);
+        else f(Tag{}, (Index)(begin + (Index)i), u, true);
+      }
+    }
+    __syncthreads();  // vals / s_tile reused by the next tile
+  }
+  if (tid == 0) scan_counter_release(s.counter);
+}
+
+template <class Policy, class F, class Red>
+struct GenericScan {
+  using V = typename Red::value_type;
+  using Index = typename Policy::index_type;
+  using Tag = typename Policy::work_tag;
+  static constexpr int BLOCK = sizeof(V) <= 64 ? 256 : 128;
+  static constexpr int ITEMS = sizeof(V) <= 8 ? 9 : (sizeof(V) <= 16 ? 7 : (sizeof(V) <= 32 ? 5 : 3));
+  static constexpr int TILE = BLOCK * ITEMS;
+  static constexpr size_t SMEM = (size_t)(TILE + 33) * sizeof(V);
+  static_assert(SMEM <= 200 * 1024, "parallel_scan value_type too large for the shared-memory tile");
+
+  static int run(const Policy& policy, const F& f, const Red& red, V* total_host, V* total_dev) {
+    b200_instance* inst = policy.space().impl_instance();
+    HostRuntime rt(inst);
+    int rc;
+    int64 n = (int64)(policy.end() - policy.begin());
+    if (n <= 0) {  // empty range: the total is the identity
+      V t;
+      red.init(t);
+      if (total_host) *total_host = t;
+      if (total_dev && (rc = b200_memcpy_h2d_async(inst, total_dev, &t, sizeof(V)))) return rc;
+      if (total_dev) return rt.fence("kb200::parallel_scan (empty)");
+      return 0;
+    }
+    auto k = generic_scan_kernel<F, Tag, Index, Red, BLOCK, ITEMS>;
+    static int bps = 0;
+    if (bps == 0) {
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, BLOCK, SMEM);
+      if (bps < 1) bps = 1;
+    }
+    const int64 ntiles = (n + TILE - 1) / TILE;
+    const int64 cap = (int64)rt.sm_count() * bps;
+    const int grid = (int)(ntiles < cap ? ntiles : cap);
+
+    GenericScanScratch<V> s;
+    void *st = nullptr, *vals = nullptr;
+    if ((rc = b200_scratch_get(inst, B200_SCRATCH_SCAN_STATUS, (size_t)ntiles * 8, &st, nullptr))) return rc;
+    if ((rc = b200_scratch_get(inst, B200_SCRATCH_SCAN_VALUES, (size_t)ntiles * 2 * sizeof(V) + 256, &vals, nullptr))) return rc;
+    s.status = reinterpret_cast<unsigned long long*>(st);
+    s.agg = reinterpret_cast<V*>(vals);
+    s.incl = s.agg + ntiles;
+    uint64_t epoch = 0, cbase = 0;
+    if ((rc = b200_scan_begin(inst, (uint64_t)ntiles + (uint64_t)grid, &epoch, &cbase, &s.counter))) return rc;
+    s.epoch = epoch;
+    s.counter_base = cbase;
+    void *slot_dev = nullptr, *slot_host = nullptr, *unused_p = nullptr;
+    unsigned* unused_t = nullptr;
+    if (total_host && (rc = rt.reduce_scratch(0, sizeof(V), true, &unused_p, &unused_t, &slot_dev, &slot_host))) return rc;
+    V* t0 = total_host ? reinterpret_cast<V*>(slot_dev) : total_dev;
+    V* t1 = total_host ? total_dev : nullptr;
+    k<<<grid, BLOCK, SMEM, rt.stream()>>>(f, red, policy.begin(), n, ntiles, s, t0, t1);
+    if ((rc = rt.check_launch("kb200::generic_scan_kernel"))) return rc;
+    if (total_host) {
+      if ((rc = rt.fence("kb200::parallel_scan: fence to hand the total to the host"))) return rc;
+      memcpy(total_host, slot_host, sizeof(V));
+    }
+    return 0;
+  }
+};
+
+}  // namespace Impl
+}  // namespace kb200
+#endif

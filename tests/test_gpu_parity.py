@@ -146,9 +146,9 @@ def test_scan_matches_golden_and_port(space, port, n):
     assert float(total).hex() == g["total"] and W.checksum64(vy.to_host()) == g["checksum"]
 
 
-@pytest.mark.parametrize("n", (1, 4607, 4608, 4609, 9216, 1 << 20, (1 << 22) + 12345))
+@pytest.mark.parametrize("n", (1, 2303, 2304, 2305, 4607, 4608, 4609, 9216, 1 << 20, (1 << 22) + 12345))
 def test_scan_closed_form_tile_edges_inplace_and_unaligned(space, n):
-    # TestParallelScanRangePolicy.hpp:66-84 closed forms; sizes straddle the 4608-element tile
+    # TestParallelScanRangePolicy.hpp:66-84 closed forms; sizes straddle the 2304- and 4608-element tiles
     i = np.arange(n, dtype=np.int64)
     v = space.view_from_host(i)
     total = space.parallel_scan(v, v, inclusive=False)  # in place
@@ -169,6 +169,22 @@ def test_scan_closed_form_tile_edges_inplace_and_unaligned(space, n):
     t = space.parallel_scan(space.view_from_host(x32), y32)
     ref = np.concatenate([[0], np.cumsum(x32[:-1], dtype=np.int64)]).astype(np.int32)
     assert t == int(x32.sum()) and np.array_equal(y32.to_host(), ref)
+
+
+def test_scan_uniform_kernel_on_aligned_views(space, port):
+    """The non-warp-specialised kernel normally serves unaligned Views only; force it on aligned ones too."""
+    import kokkos_b200 as kb
+    for ws in (0, 1):
+      kb.tune_set("scan.ws", ws); kb.tune_set("scan.block", 256); kb.tune_set("scan.nbuf", 2); kb.tune_set("scan.lbw", 2)
+      try:
+        for n in (4608, 100003, 1 << 20):
+            x = W.c3_wrap(n)
+            vy = space.view(n, np.int64)
+            total = space.parallel_scan(space.view_from_host(x), vy, seed=5)
+            py, pt = port.scan(x, False, 5, T)
+            assert total == pt and np.array_equal(vy.to_host(), py)
+      finally:
+        kb.tune_set("scan.ws", 2); kb.tune_set("scan.block", 128); kb.tune_set("scan.nbuf", 4); kb.tune_set("scan.lbw", 1)
 
 
 def test_scan_many_launches_reuse_descriptor_arena(space):
