@@ -176,6 +176,13 @@ int b200_atomic_add_f64(b200_instance*, double* table, int64_t table_len, const 
 int b200_spmv_crs_f64(b200_instance*, int64_t nrows, const int64_t* row_map, const int32_t* col_idx,
                       const double* values, const double* x, double* y);
 
+/* ---- host-buffer forms: deep_copy(device,host) -> pattern -> deep_copy(host,device) as ONE chunked, double-buffered
+ *      pipeline (H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c; chunks are chained on the
+ *      device, no host sync inside).  Replaces the user-level sequence around core/src/Kokkos_CopyViews.hpp:897-1100.
+ *      Host buffers should be pinned (b200_malloc_host_pinned).  Blocking. ---- */
+int b200_reduce_sum_f64_host(b200_instance*, const double* host_x, int64_t n, double* result);
+int b200_scan_excl_i64_host(b200_instance*, const int64_t* host_x, int64_t* host_y, int64_t n, int64_t seed, int64_t* total);
+
 /* ---- tuning knobs (benchmark harness only; defaults are the shipped configuration) ---- */
 int b200_tune_set(const char* key, int value);
 int b200_tune_get(const char* key, int* value);

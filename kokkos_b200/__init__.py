@@ -93,6 +93,8 @@ def load_library() -> ctypes.CDLL:
         "b200_atomic_add_f64": [P, P, c_int64, P, P, c_int64],
         "b200_spmv_crs_f64": [P, c_int64, P, P, P, P, P],
         "b200_scan_excl_i64_seed_dev": [P, P, P, c_int64, P, P],
+        "b200_reduce_sum_f64_host": [P, P, c_int64, P],
+        "b200_scan_excl_i64_host": [P, P, P, c_int64, c_int64, P],
     }
     for name in ("sum_f64", "sum_f32", "sum_i64", "sum_i32", "min_f64", "max_f64", "min_i64", "max_i64", "min_i32",
                  "max_i32", "minmax_f64"):
@@ -291,6 +293,17 @@ class B200:
 
     def parallel_scan_seed_dev(self, x: View, y: View, seed_dev: int, total_dev: int = 0) -> None:
         _check(self.lib.b200_scan_excl_i64_seed_dev(self.handle, x.ptr, y.ptr, x.n, seed_dev, total_dev or None))
+
+    # ---- host-buffer forms (chunked H2D / kernel / D2H pipeline inside the library) ----
+    def parallel_reduce_sum_host(self, host_ptr: int, n: int) -> float:
+        out = c_double()
+        _check(self.lib.b200_reduce_sum_f64_host(self.handle, host_ptr, n, byref(out)))
+        return out.value
+
+    def parallel_scan_host(self, host_x_ptr: int, host_y_ptr: int, n: int, seed: int = 0) -> int:
+        out = c_int64()
+        _check(self.lib.b200_scan_excl_i64_host(self.handle, host_x_ptr, host_y_ptr, n, seed, byref(out)))
+        return out.value
 
     # ---- parallel_for (stream) ----
     def stream_set(self, a: View, value: float) -> None:
