@@ -186,33 +186,26 @@ def main():
         xi[c:c + m] = (h % 7) - 3
         del idx, h
     vxd, vxi, vyi = space.wrap(xd.data_ptr(), n, np.float64), space.wrap(xi.data_ptr(), n, np.int64), space.wrap(yi.data_ptr(), n, np.int64)
+    from kokkos_b200.sharded import ShardedB200
+    sp = ShardedB200(space, coll_device=dev)   # the range-sharded layer: local kernels + NCCL combines (world 1: no collectives)
     red_dev = torch.zeros(1, dtype=torch.float64, device=dev)
     tot_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-    seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-    gathered = torch.zeros(world, dtype=torch.int64, device=dev)
+    # our kernels per step: reduce(xd) + scan at N=1; reduce(xd) + shard-total reduce(xi) + seeded scan at N>1
     launches_per_step = 2 if not distributed else 3
 
     scan_ev = []
 
     def step(record=False):
-        # parallel_reduce Sum<double>: result stays on the device (View result => asynchronous)
-        space.parallel_reduce_sum(vxd, result_dev=red_dev.data_ptr(), blocking=False)
-        if distributed:
-            dist.all_reduce(red_dev, op=dist.ReduceOp.SUM)
-            # distributed scan: shard totals -> all-gather -> exclusive prefix of lower ranks -> seeded local scan
-            space.parallel_reduce_sum(vxi, result_dev=tot_dev.data_ptr(), blocking=False)
-            dist.all_gather_into_tensor(gathered, tot_dev)
-            seed_dev.copy_(gathered[:rank].sum() if rank else torch.zeros((), dtype=torch.int64, device=dev))
+        # parallel_reduce Sum<double>: result stays on the device (View result => asynchronous); N>1: + NCCL all-reduce
+        sp.reduce_sum_async(vxd, out=red_dev)
+        # parallel_scan: N>1 = shard totals -> NCCL all-gather -> seeded local scan (the kernel sums the lower ranks' totals)
+        hooks = None
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(side)
-        if distributed:
-            space.parallel_scan_seed_dev(vxi, vyi, seed_dev.data_ptr(), tot_dev.data_ptr())
-        else:
-            space.parallel_scan(vxi, vyi, total_dev=tot_dev.data_ptr(), blocking=False)
-        if record:
-            e1.record(side)
+            hooks = (lambda: e0.record(side), lambda: e1.record(side))
             scan_ev.append((e0, e1))
+        totals = sp.scan_exclusive_async(vxi, vyi, total_out=tot_dev, around_scan_kernel=hooks)
+        return totals
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -231,7 +224,10 @@ def main():
         dist.all_reduce(t)
         exp_red = float(t.item())
     assert got_red == exp_red, ("reduce mismatch", got_red, exp_red)
-    chk = torch.cumsum(xi[: 1 << 20], 0) - xi[: 1 << 20] + int(seed_dev.item() if distributed else 0)
+    totals = step()
+    torch.cuda.synchronize(dev)
+    seed_exp = int(totals[:rank].sum().item()) if distributed else 0
+    chk = torch.cumsum(xi[: 1 << 20], 0) - xi[: 1 << 20] + seed_exp
     assert torch.equal(chk, yi[: 1 << 20]), "scan mismatch in the first 2^20 outputs"
     assert int(tot_dev.item()) == int(xi.sum().item()), "scan total mismatch"
     del chk

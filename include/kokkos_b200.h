@@ -144,6 +144,10 @@ int b200_scan_excl_i32(b200_instance*, const int32_t* x, int32_t* y, int64_t n, 
 /* as b200_scan_excl_i64 but the seed is read from device memory when the kernel runs
  * (lets a distributed scan chain reduce -> all-gather -> scan on one stream with no host sync) */
 int b200_scan_excl_i64_seed_dev(b200_instance*, const int64_t* x, int64_t* y, int64_t n, const int64_t* seed_dev, int64_t* total_dev);
+/* seed = seeds_dev[0] + ... + seeds_dev[nseeds-1], summed by the kernel: a rank of a range-sharded scan passes the
+ * all-gathered shard totals and nseeds = its rank (nseeds == 0 => seed 0), so the NCCL all-gather output feeds the scan
+ * directly -- no host round trip and no helper kernel between the collective and the scan */
+int b200_scan_excl_i64_seeds_dev(b200_instance*, const int64_t* x, int64_t* y, int64_t n, const int64_t* seeds_dev, int nseeds, int64_t* total_dev);
 
 /* parallel_for over RangePolicy, the benchmarks/stream kernels
  * (benchmarks/stream/stream-kokkos.cpp:55-77): replaces ParallelFor<F,RangePolicy,Cuda>

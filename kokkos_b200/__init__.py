@@ -93,6 +93,7 @@ def load_library() -> ctypes.CDLL:
         "b200_atomic_add_f64": [P, P, c_int64, P, P, c_int64],
         "b200_spmv_crs_f64": [P, c_int64, P, P, P, P, P],
         "b200_scan_excl_i64_seed_dev": [P, P, P, c_int64, P, P],
+        "b200_scan_excl_i64_seeds_dev": [P, P, P, c_int64, P, c_int, P],
         "b200_reduce_sum_f64_host": [P, P, c_int64, P],
         "b200_scan_excl_i64_host": [P, P, P, c_int64, c_int64, P],
     }
@@ -293,6 +294,10 @@ class B200:
 
     def parallel_scan_seed_dev(self, x: View, y: View, seed_dev: int, total_dev: int = 0) -> None:
         _check(self.lib.b200_scan_excl_i64_seed_dev(self.handle, x.ptr, y.ptr, x.n, seed_dev, total_dev or None))
+
+    def parallel_scan_seeds_dev(self, x: View, y: View, seeds_dev: int, nseeds: int, total_dev: int = 0) -> None:
+        """Exclusive int64 scan seeded with sum(seeds_dev[0:nseeds]) read on the device (distributed scan, rank = nseeds)."""
+        _check(self.lib.b200_scan_excl_i64_seeds_dev(self.handle, x.ptr, y.ptr, x.n, seeds_dev or None, nseeds, total_dev or None))
 
     # ---- host-buffer forms (chunked H2D / kernel / D2H pipeline inside the library) ----
     def parallel_reduce_sum_host(self, host_ptr: int, n: int) -> float:

@@ -11,7 +11,7 @@ using kb200::Impl::ContigScanLaunch;
 
 namespace {
 template <class T, bool INCL>
-int scan_entry(b200_instance* I, const char* where, const T* x, T* y, int64_t n, T seed, const T* seed_dev, T* th, T* td) {
+int scan_entry(b200_instance* I, const char* where, const T* x, T* y, int64_t n, T seed, const T* seed_dev, T* th, T* td, int nseeds = 1) {
   B200_CHECK_INST(I, where);
   if (n < 0) return b200_set_error(B200_EINVAL, where, "negative length");
   if (n > 0 && (!x || !y)) return b200_set_error(B200_EINVAL, where, "x or y is NULL");
@@ -22,18 +22,18 @@ int scan_entry(b200_instance* I, const char* where, const T* x, T* y, int64_t n,
   const int ws = aligned ? b200_tune("scan.ws", 2) : 0;
   const int sleep_ns = b200_tune("scan.sleep", 0), dbg = b200_tune("scan.dbg", 0);
 #define CFG(BL, NV, NB, LB) \
-  if (!ws && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 0>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg);
+  if (!ws && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 0>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg, nseeds);
 #define ZCFG(BL, NV, NB, LB) \
-  if (ws == 4 && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 4>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg);
+  if (ws == 4 && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 4>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg, nseeds);
 #define YCFG(BL, NV, NB, LB) \
-  if (ws == 3 && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 3>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg);
+  if (ws == 3 && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 3>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg, nseeds);
 #define XCFG(BL, NV, NB, LB) \
-  if (ws == 2 && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 2>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg);
+  if (ws == 2 && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 2>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg, nseeds);
 #define WCFG(BL, NV, NB, LB) \
-  if (ws == 1 && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 1>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg);
+  if (ws == 1 && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 1>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg, nseeds);
   XCFG(128, 9, 4, 1)   // shipped: 5 variants x ~90 configurations measured, profiles/r01_scan_probe_v*.log
   WCFG(256, 9, 2, 2)
-  if (!ws) return ContigScanLaunch<T, 256, 9, 2, 2, INCL, 0>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg);
+  if (!ws) return ContigScanLaunch<T, 256, 9, 2, 2, INCL, 0>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg, nseeds);
 #ifdef B200_SWEEP
   if constexpr (sizeof(T) == 8 && !INCL) {
     CFG(256, 9, 2, 1) CFG(256, 9, 2, 4) CFG(256, 9, 3, 2) CFG(256, 9, 3, 4)
@@ -92,6 +92,11 @@ int b200_scan_excl_i32(b200_instance* I, const int32_t* x, int32_t* y, int64_t n
 int b200_scan_excl_i64_seed_dev(b200_instance* I, const int64_t* x, int64_t* y, int64_t n, const int64_t* seed_dev, int64_t* td) {
   if (!seed_dev) return b200_set_error(B200_EINVAL, "b200_scan_excl_i64_seed_dev", "seed_dev is NULL");
   return scan_entry<int64, false>(I, "b200_scan_excl_i64_seed_dev", (const int64*)x, (int64*)y, n, 0, (const int64*)seed_dev, nullptr, (int64*)td);
+}
+int b200_scan_excl_i64_seeds_dev(b200_instance* I, const int64_t* x, int64_t* y, int64_t n, const int64_t* seeds_dev, int nseeds, int64_t* td) {
+  if (nseeds < 0 || (nseeds > 0 && !seeds_dev)) return b200_set_error(B200_EINVAL, "b200_scan_excl_i64_seeds_dev", "bad seed array");
+  if (nseeds == 0) return scan_entry<int64, false>(I, "b200_scan_excl_i64_seeds_dev", (const int64*)x, (int64*)y, n, 0, nullptr, nullptr, (int64*)td);
+  return scan_entry<int64, false>(I, "b200_scan_excl_i64_seeds_dev", (const int64*)x, (int64*)y, n, 0, (const int64*)seeds_dev, nullptr, (int64*)td, nseeds);
 }
 }  // extern "C"
 

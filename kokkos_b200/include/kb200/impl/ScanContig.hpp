@@ -63,7 +63,8 @@ struct ScanContigParams {
   int64 n;
   int64 ntiles;
   T seed;
-  const T* seed_dev;  // if non-null, read instead of `seed`
+  const T* seed_dev;  // if non-null, the seed is the sum of seed_dev[0..seed_count) read when the kernel runs
+  int seed_count;     // (a distributed scan passes the all-gathered shard totals and its rank)
   ScanDesc16* desc;
   unsigned long long epoch;
   unsigned long long* counter;
@@ -74,6 +75,14 @@ struct ScanContigParams {
   int spin_sleep_ns;          // back-off between polls of an unpublished predecessor (0 = none)
   int dbg_flags;              // tools/sweep.py experiments only: 1 = skip look-back, 2 = skip the scan (pure copy)
 };
+
+template <class T>
+KB200_DEVICE_FUNCTION T scan_seed(const ScanContigParams<T>& p) {
+  if (!p.seed_dev) return p.seed;
+  T s = T(0);
+  for (int k = 0; k < p.seed_count; ++k) s += p.seed_dev[k];
+  return s;
+}
 
 // called by ONE thread per CTA once the CTA will take no more tile ids: the last CTA re-arms the counters
 KB200_DEVICE_FUNCTION void scan_counter_release(unsigned long long* counter) {
@@ -194,7 +203,7 @@ __global__ void __launch_bounds__(BLOCK) contig_scan_kernel(const ScanContigPara
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   KB200_STATS_DECL;
-  const T seed = p.seed_dev ? *p.seed_dev : p.seed;
+  const T seed = scan_seed(p);
 
   if (tid == 0) {
 #pragma unroll
@@ -435,7 +444,7 @@ __global__ void __launch_bounds__(CBLOCK + 32) contig_scan_ws_kernel(const ScanC
   }
 
   // ================= compute warps =================
-  const T seed = p.seed_dev ? *p.seed_dev : p.seed;
+  const T seed = scan_seed(p);
   for (int64 j = 0;; ++j) {
     const int st = (int)(j % NSTAGE);
     ptx::mbar_wait(&full[st], (unsigned)((j / NSTAGE) & 1));
@@ -677,7 +686,7 @@ __global__ void __launch_bounds__(CBLOCK + 96) contig_scan_ws2_kernel(const Scan
   }
 
   // ================= compute warps =================
-  const T seed = p.seed_dev ? *p.seed_dev : p.seed;
+  const T seed = scan_seed(p);
   for (int64 j = 0;; ++j) {
     const int st = (int)(j % NSTAGE);
     const unsigned par = (unsigned)((j / NSTAGE) & 1);
@@ -898,7 +907,7 @@ __global__ void __launch_bounds__(CBLOCK + 128) contig_scan_ws3_kernel(const Sca
   }
 
   // ================= compute warps =================
-  const T seed = p.seed_dev ? *p.seed_dev : p.seed;
+  const T seed = scan_seed(p);
   for (int64 j = 0;; ++j) {
     const int st = (int)(j % NSTAGE);
     const unsigned par = (unsigned)((j / NSTAGE) & 1);
@@ -1124,7 +1133,7 @@ __global__ void __launch_bounds__(CBLOCK + 96 + 32 * NSTAGE) contig_scan_ws4_ker
   }
 
   // ================= compute warps =================
-  const T seed = p.seed_dev ? *p.seed_dev : p.seed;
+  const T seed = scan_seed(p);
   for (int64 j = 0;; ++j) {
     const int st = (int)(j % NSTAGE);
     const unsigned par = (unsigned)((j / NSTAGE) & 1);
@@ -1216,7 +1225,7 @@ struct ContigScanLaunch {
   }
 
   static int run(b200_instance* inst, const T* x, T* y, int64 n, T seed, const T* seed_dev, T* total_host, T* total_dev,
-                 int blocks_per_sm_cap = 0, int spin_sleep_ns = 0, int dbg_flags = 0) {
+                 int blocks_per_sm_cap = 0, int spin_sleep_ns = 0, int dbg_flags = 0, int seed_count = 1) {
     HostRuntime rt(inst);
     int rc;
     if (n == 0) {  // empty range: total = identity, nothing written
@@ -1234,7 +1243,7 @@ struct ContigScanLaunch {
     const int grid = (int)(ntiles < max_grid ? ntiles : max_grid);
 
     ScanContigParams<T> p;
-    p.x = x; p.y = y; p.n = n; p.ntiles = ntiles; p.seed = seed; p.seed_dev = seed_dev;
+    p.x = x; p.y = y; p.n = n; p.ntiles = ntiles; p.seed = seed; p.seed_dev = seed_dev; p.seed_count = seed_count;
     void* desc = nullptr;
     if ((rc = b200_scratch_get(inst, B200_SCRATCH_SCAN_DESC, (size_t)ntiles * sizeof(ScanDesc16), &desc, nullptr))) return rc;
     p.desc = reinterpret_cast<ScanDesc16*>(desc);
