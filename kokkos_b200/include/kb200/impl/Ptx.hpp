@@ -18,6 +18,9 @@ KB200_DEVICE_FUNCTION void fence_mbar_init() { asm volatile("fence.mbarrier_init
 KB200_DEVICE_FUNCTION void mbar_expect_tx(void* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+KB200_DEVICE_FUNCTION void mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 KB200_DEVICE_FUNCTION bool mbar_try_wait(void* bar, unsigned parity) {
   unsigned ok;
   asm volatile(

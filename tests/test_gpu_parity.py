@@ -255,6 +255,44 @@ def test_stencil_minmaxloc_bit_exact(space, port, dims):
         assert W.checksum64(vout.to_host()) == C[key]["v_checksum"]
 
 
+@pytest.mark.parametrize("dims", ((512, 11, 9), (4, 4, 4), (6, 3, 3), (258, 19, 37), (64, 10, 70), (33, 12, 9), (514, 5, 4)))
+@pytest.mark.parametrize("store", (False, True))
+def test_stencil_both_kernels_edge_shapes(space, port, dims, store):
+    """Even n0 <= 512 takes the TMA plane-marching kernel (partial j tiles, short k chunks, i edges); odd / wide n0 the
+    row-per-warp kernel.  Random data: every value and both locations bit-exact vs the oracle."""
+    n = dims[0] * dims[1] * dims[2]
+    u = W.c1_uniform(n, seed=dims[0] * 131 + dims[1])
+    vout = space.view(n, np.float64) if store else None
+    if store:
+        space.lib.b200_memset_async(space.handle, vout.ptr, 0, vout.nbytes)
+    r = space.stencil7_minmaxloc(space.view_from_host(u), *dims, 0.5, 0.125, v_out=vout)
+    q, pv = port.stencil7(u, *dims, 0.5, 0.125, want_v=True)
+    assert (r.min_val, r.max_val, r.min_loc, r.max_loc) == (q.min_val, q.max_val, q.min_loc, q.max_loc)
+    if store:
+        assert np.array_equal(vout.to_host(), pv)
+
+
+@pytest.mark.parametrize("dims", ((64, 20, 18), (33, 9, 9)))
+def test_stencil_ties_keep_the_lowest_location(space, port, dims):
+    """Equal extrema: the first location in the reference's host iteration order (i slowest, k fastest) wins, i.e. the
+    lowest flattened location -- a constant field (every interior point ties) and a field with duplicated extrema."""
+    n = dims[0] * dims[1] * dims[2]
+    for u in (np.full(n, 1.5), np.tile(np.array([1.0, -2.0, 3.0, 0.5, 3.0, -2.0]), n // 6 + 1)[:n].copy()):
+        r = space.stencil7_minmaxloc(space.view_from_host(u), *dims, 0.5, 0.125)
+        q, _ = port.stencil7(u, *dims, 0.5, 0.125)
+        assert (r.min_val, r.max_val, r.min_loc, r.max_loc) == (q.min_val, q.max_val, q.min_loc, q.max_loc)
+
+
+def test_stencil_unaligned_view_falls_back(space, port):
+    dims = (64, 12, 10)
+    n = dims[0] * dims[1] * dims[2]
+    u = W.c1_uniform(n + 1)
+    base = space.view_from_host(u)
+    r = space.stencil7_minmaxloc(base.subview(1, n + 1), *dims, 0.5, 0.125)   # 8-byte aligned only
+    q, _ = port.stencil7(u[1:], *dims, 0.5, 0.125)
+    assert (r.min_val, r.max_val, r.min_loc, r.max_loc) == (q.min_val, q.max_val, q.min_loc, q.max_loc)
+
+
 def test_stencil_empty_interior_yields_identity(space):
     u = space.view_from_host(np.ones(2 * 5 * 5))
     r = space.stencil7_minmaxloc(u, 2, 5, 5, 1.0, 1.0)
