@@ -151,15 +151,17 @@ struct StencilUnit {
 // One plane step of one unit: prev/cur are the k-1/k planes of the unit's points (registers), nxt receives the k+1 plane.
 // P = stage of plane k (j- and i-halos), N = stage of plane k+1.  FULL: every row of the tile is interior (no row masks).
 // vplane = vout + n0*(j0 + n1*k) (tile/plane base of the output).
-template <bool STORE, bool FULL, int N0T>
-KB200_DEVICE_FUNCTION void stencil_unit_step(const double* __restrict__ P, const double* __restrict__ N, const StencilUnit& un, int n0rt,
+template <bool STORE, bool FULL, int N0T, bool SLOW>
+KB200_DEVICE_FUNCTION bool stencil_unit_step(const double* __restrict__ P, const double* __restrict__ N, const StencilUnit& un, int n0rt,
                                              int pad, int nrows, const double2 (&prev)[2], const double2 (&cur)[2], double2 (&nxt)[2],
-                                             double c0, double c1, int j0, int k, int n1, int n2, double* __restrict__ vplane, V& acc) {
+                                             double c0, double c1, int j0, int k, int n1, int n2, double* __restrict__ vplane, V& acc, double tmin, double tmax) {
   const int n0 = N0T ? N0T : n0rt;
   const double* Pu = P + un.off;
   const double* Nu = N + un.off;
-  nxt[0] = *reinterpret_cast<const double2*>(Nu);
-  nxt[1] = *reinterpret_cast<const double2*>(Nu + n0);
+  if constexpr (!SLOW) {
+    nxt[0] = *reinterpret_cast<const double2*>(Nu);
+    nxt[1] = *reinterpret_cast<const double2*>(Nu + n0);
+  }
   const double2 ym = *reinterpret_cast<const double2*>(Pu - n0);
   const double2 yp = *reinterpret_cast<const double2*>(Pu + 2 * n0);
   const double xm0 = P[un.xl], xp0 = P[un.xr];
@@ -174,7 +176,7 @@ KB200_DEVICE_FUNCTION void stencil_unit_step(const double* __restrict__ P, const
     const int row = un.off / n0 - 1;
     vm &= (row < nrows ? 3u : 0u) | (row + 1 < nrows ? 12u : 0u);
   }
-  if constexpr (STORE) {
+  if constexpr (STORE && !SLOW) {
     double* o = vplane + (un.off - n0);  // = i0 + n0*row
     if ((vm & 3u) == 3u) *reinterpret_cast<double2*>(o) = make_double2(v00, v01);
     else { if (vm & 1u) o[0] = v00; if (vm & 2u) o[1] = v01; }
@@ -182,20 +184,36 @@ KB200_DEVICE_FUNCTION void stencil_unit_step(const double* __restrict__ P, const
     if ((vm & 12u) == 12u) *reinterpret_cast<double2*>(o) = make_double2(v10, v11);
     else { if (vm & 4u) o[0] = v10; if (vm & 8u) o[1] = v11; }
   }
-  bool hit;
-  if constexpr (FULL) {
-    hit = stencil_hit(v00, v01, v10, v11, acc.min_val, acc.max_val);  // boundary columns are NaN already
-  } else {  // partial tile: rows past the end hold stale data -> poison them
-    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-    hit = stencil_hit((vm & 1u) ? v00 : qnan, (vm & 2u) ? v01 : qnan, (vm & 4u) ? v10 : qnan, (vm & 8u) ? v11 : qnan, acc.min_val, acc.max_val);
-  }
-  if (hit) {  // rare: a new extremum or a tie -> exact rule with locations
+  if constexpr (SLOW) {  // rare re-evaluation of a step in which some lane saw a candidate: exact rule with locations
     const int row = un.off / n0 - 1, i0 = un.off - (row + 1) * n0, j = j0 + row;
     if (vm & 1u) stencil_update(acc, v00, i0, j, k, n1, n2);
     if (vm & 2u) stencil_update(acc, v01, i0 + 1, j, k, n1, n2);
     if (vm & 4u) stencil_update(acc, v10, i0, j + 1, k, n1, n2);
     if (vm & 8u) stencil_update(acc, v11, i0 + 1, j + 1, k, n1, n2);
+    return false;
   }
+  bool hit;
+  if constexpr (FULL) {
+    hit = stencil_hit(v00, v01, v10, v11, tmin, tmax);  // boundary columns are NaN already
+  } else {  // partial tile: rows past the end hold stale data -> poison them
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    hit = stencil_hit((vm & 1u) ? v00 : qnan, (vm & 2u) ? v01 : qnan, (vm & 4u) ? v10 : qnan, (vm & 8u) ? v11 : qnan, tmin, tmax);
+  }
+  return hit;
+}
+
+// Warp-shared thresholds: a point can only be the global extremum if it reaches the best value ANY lane of the warp has
+// seen (ties included, hence <= / >= in the hit test).  With per-thread thresholds each thread's ~2500 points trigger
+// ~2 ln(2500) updates and some lane of a warp hit in 30 % of the steps (profiles/r01_stencil_v3_ncu.txt).
+KB200_DEVICE_FUNCTION void stencil_refresh_thresholds(const V& acc, double& tmin, double& tmax) {
+  double a = acc.min_val, b = acc.max_val;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double a2 = shfl_xor(a, d), b2 = shfl_xor(b, d);
+    a = a2 < a ? a2 : a;
+    b = b2 > b ? b2 : b;
+  }
+  tmin = a; tmax = b;
 }
 
 struct StencilTmaParams {
@@ -204,14 +222,52 @@ struct StencilTmaParams {
   int n0, n1, n2;
   int kc, tiles_j, tiles_k;
   double c0, c1;
+  int dbg;  // tools/stencil_probe.py experiments only: 1 = consumers skip the arithmetic (pure data movement), 2 = no data movement (pure arithmetic on stale smem)
 };
 
 // stage = (BJ+2) rows of n0 doubles + a pad of n0+2 doubles whose elements [0,1] and [n0,n0+1] are NaN
 KB200_FUNCTION constexpr int stencil_stage_elems(int bj, int n0) { return (bj + 2) * n0 + n0 + 2; }
 
 // BJ rows per tile (even), NS stages, CT consumer threads (+ one producer warp); N0T = n0 when known at compile time (else 0)
-template <int BJ, int NS, int CT, bool STORE, int N0T>
-__global__ void __launch_bounds__(CT + 32, 1) stencil7_tma_kernel(const StencilTmaParams p, const ReduceScratch scratch) {
+// cursor over the block's sequence of plane slabs (tile-major, k inside): used by the dedicated producer warp, or -- when
+// every warp computes (PW = false) -- by thread 0, which issues slab g+NS-1 right after it has released slab g.
+template <int BJ, int NS>
+struct StencilProducer {
+  int tile, kk, ke, j0;
+  unsigned x;  // index of the next slab to issue
+  unsigned bytes;
+  KB200_DEVICE_FUNCTION void open_tile(const StencilTmaParams& p, int n0) {
+    const int tj = tile % p.tiles_j, tk = tile / p.tiles_j;
+    const int k0 = 1 + tk * p.kc;
+    j0 = 1 + tj * BJ;
+    kk = k0 - 1;
+    ke = min(k0 + p.kc, p.n2 - 1);                               // interior planes [k0, ke)
+    const int rows = min(j0 + BJ, p.n1 - 1) - (j0 - 1) + 1;      // rows j0-1 .. min(j0+BJ, n1-1)
+    bytes = (unsigned)rows * (unsigned)n0 * 8u;
+  }
+  KB200_DEVICE_FUNCTION void start(const StencilTmaParams& p, int n0) {
+    tile = blockIdx.x; x = 0;
+    if (tile < p.tiles_j * p.tiles_k) open_tile(p, n0);
+  }
+  // issue the next slab (waits until its stage's previous occupant was released by every consumer warp)
+  KB200_DEVICE_FUNCTION void issue(const StencilTmaParams& p, int n0, double* stages, int stage_elems, unsigned long long* full,
+                                   unsigned long long* empty) {
+    if (tile >= p.tiles_j * p.tiles_k) return;
+    if (p.dbg == 2) { tile = p.tiles_j * p.tiles_k; return; }  // probe: no data movement
+    const unsigned s = x % NS, use = x / NS;
+    if (use > 0) ptx::mbar_wait(&empty[s], (use & 1u) ^ 1u);
+    ptx::mbar_expect_tx(&full[s], bytes);
+    ptx::bulk_g2s(stages + (size_t)s * stage_elems, p.u + (size_t)n0 * ((size_t)(j0 - 1) + (size_t)p.n1 * kk), bytes, &full[s]);
+    ++x;
+    if (++kk > ke) {
+      tile += gridDim.x;
+      if (tile < p.tiles_j * p.tiles_k) open_tile(p, n0);
+    }
+  }
+};
+
+template <int BJ, int NS, int CT, bool STORE, int N0T, bool PW>
+__global__ void __launch_bounds__(CT + (PW ? 32 : 0), 1) stencil7_tma_kernel(const StencilTmaParams p, const ReduceScratch scratch) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ __align__(16) unsigned char red_smem[32 * sizeof(V)];
   constexpr int CW = CT / 32;
@@ -232,29 +288,20 @@ __global__ void __launch_bounds__(CT + 32, 1) stencil7_tma_kernel(const StencilT
     double* q = stages + (size_t)tid * stage_elems + pad;
     q[0] = qnan; q[1] = qnan; q[n0] = qnan; q[n0 + 1] = qnan;
   }
+  if (p.dbg == 2)  // probe: arithmetic on resident pseudo-random data
+    for (int q = tid; q < NS * stage_elems; q += blockDim.x) stages[q] = (double)((q * 2654435761u) >> 8) * (1.0 / 16777216.0);
   __syncthreads();
   const StencilRed red;
   V acc;
   red.init(acc);
   const int ntiles = p.tiles_j * p.tiles_k;
 
-  if (warp == CW) {
-    // ---------------- producer: one bulk copy per plane slab
+  StencilProducer<BJ, NS> prod;
+  if (PW && warp == CW) {
+    // ---------------- dedicated producer warp: one bulk copy per plane slab, as far ahead as the ring allows
     if (lane == 0) {
-      unsigned pos = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int tj = tile % p.tiles_j, tk = tile / p.tiles_j;
-        const int j0 = 1 + tj * BJ, k0 = 1 + tk * p.kc;
-        const int ke = min(k0 + p.kc, n2 - 1);                 // interior planes [k0, ke)
-        const int rows = min(j0 + BJ, n1 - 1) - (j0 - 1) + 1;  // rows j0-1 .. min(j0+BJ, n1-1)
-        const unsigned bytes = (unsigned)rows * (unsigned)n0 * 8u;
-        for (int kk = k0 - 1; kk <= ke; ++kk, ++pos) {
-          const unsigned s = pos % NS, use = pos / NS;
-          if (use > 0) ptx::mbar_wait(&empty[s], (use & 1u) ^ 1u);
-          ptx::mbar_expect_tx(&full[s], bytes);
-          ptx::bulk_g2s(stages + (size_t)s * stage_elems, p.u + (size_t)n0 * ((size_t)(j0 - 1) + (size_t)n1 * kk), bytes, &full[s]);
-        }
-      }
+      prod.start(p, n0);
+      while (prod.tile < ntiles) prod.issue(p, n0, stages, stage_elems, full, empty);
     }
   } else {
     // ---------------- consumers
@@ -274,7 +321,18 @@ __global__ void __launch_bounds__(CT + 32, 1) stencil7_tma_kernel(const StencilT
       actmask |= act ? (1u << m) : 0u;
     }
     const double c0 = p.c0, c1 = p.c1;
+    double tmin = acc.min_val, tmax = acc.max_val;  // warp-shared candidate thresholds (see stencil_unit_step)
     unsigned pos = 0;
+    if (!PW && tid == 0) {  // every warp computes: thread 0 doubles as the producer, NS-1 slabs ahead of its own releases
+      prod.start(p, n0);
+      for (int q = 0; q < NS - 1; ++q) prod.issue(p, n0, stages, stage_elems, full, empty);
+    }
+#define KB200_STENCIL_RELEASE(S)                                                           \
+    {                                                                                      \
+      __syncwarp();                                                                        \
+      if (lane == 0) ptx::mbar_arrive(&empty[S]);                                          \
+      if (!PW && tid == 0) prod.issue(p, n0, stages, stage_elems, full, empty);            \
+    }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int tj = tile % p.tiles_j, tk = tile / p.tiles_j;
       const int j0 = 1 + tj * BJ, k0 = 1 + tk * p.kc;
@@ -285,16 +343,15 @@ __global__ void __launch_bounds__(CT + 32, 1) stencil7_tma_kernel(const StencilT
       double2 ra[UPT][2], rb[UPT][2], rc[UPT][2];  // three rotating plane buffers: no register moves between steps
       {  // k0-1 and k0 centres -> registers
         const unsigned s0 = pos % NS, s1 = (pos + 1) % NS;
-        ptx::mbar_wait(&full[s0], (pos / NS) & 1u);
+        if (p.dbg != 2) ptx::mbar_wait(&full[s0], (pos / NS) & 1u);
         const double* P = stages + (size_t)s0 * stage_elems;
 #pragma unroll
         for (int m = 0; m < UPT; ++m) {
           ra[m][0] = *reinterpret_cast<const double2*>(P + un[m].off);
           ra[m][1] = *reinterpret_cast<const double2*>(P + un[m].off + n0);
         }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty[s0]);
-        ptx::mbar_wait(&full[s1], ((pos + 1) / NS) & 1u);
+        KB200_STENCIL_RELEASE(s0)
+        if (p.dbg != 2) ptx::mbar_wait(&full[s1], ((pos + 1) / NS) & 1u);
         const double* Q = stages + (size_t)s1 * stage_elems;
 #pragma unroll
         for (int m = 0; m < UPT; ++m) {
@@ -307,21 +364,31 @@ __global__ void __launch_bounds__(CT + 32, 1) stencil7_tma_kernel(const StencilT
       {                                                                                                                 \
         const int kk = k0 - 1 + t;                                                                                      \
         const unsigned scur = (pos + t) % NS, snext = (pos + t + 1) % NS;                                               \
-        ptx::mbar_wait(&full[snext], ((pos + t + 1) / NS) & 1u);                                                        \
+        if (p.dbg != 2) ptx::mbar_wait(&full[snext], ((pos + t + 1) / NS) & 1u);                                        \
         const double* P = stages + (size_t)scur * stage_elems;                                                          \
         const double* N = stages + (size_t)snext * stage_elems;                                                         \
         double* vplane = STORE ? p.vout + (size_t)n0 * ((size_t)j0 + (size_t)n1 * kk) : nullptr;                        \
-        if (full_tile) {                                                                                                \
+        bool hit = false;                                                                                               \
+        if (p.dbg == 1) {                                                                                               \
+        } else if (full_tile) {                                                                                         \
           _Pragma("unroll") for (int m = 0; m < UPT; ++m)                                                               \
             if ((actmask >> m) & 1u)                                                                                    \
-              stencil_unit_step<STORE, true, N0T>(P, N, un[m], n0, pad, nrows, PREV[m], CUR[m], NXT[m], c0, c1, j0, kk, n1, n2, vplane, acc); \
+              hit |= stencil_unit_step<STORE, true, N0T, false>(P, N, un[m], n0, pad, nrows, PREV[m], CUR[m], NXT[m], c0, c1, j0, kk, n1, n2, vplane, acc, tmin, tmax); \
         } else {                                                                                                        \
           _Pragma("unroll") for (int m = 0; m < UPT; ++m)                                                               \
             if ((actmask >> m) & 1u)                                                                                    \
-              stencil_unit_step<STORE, false, N0T>(P, N, un[m], n0, pad, nrows, PREV[m], CUR[m], NXT[m], c0, c1, j0, kk, n1, n2, vplane, acc); \
+              hit |= stencil_unit_step<STORE, false, N0T, false>(P, N, un[m], n0, pad, nrows, PREV[m], CUR[m], NXT[m], c0, c1, j0, kk, n1, n2, vplane, acc, tmin, tmax); \
         }                                                                                                               \
-        __syncwarp();                                                                                                   \
-        if (lane == 0) ptx::mbar_arrive(&empty[scur]);                                                                  \
+        /* one branch per STEP: the hot path stays a single basic block over all units (free interleaving) */         \
+        if (__any_sync(kFullMask, hit)) {                                                                               \
+          if (hit) {                                                                                                    \
+            _Pragma("unroll") for (int m = 0; m < UPT; ++m)                                                             \
+              if ((actmask >> m) & 1u)                                                                                  \
+                stencil_unit_step<STORE, false, N0T, true>(P, N, un[m], n0, pad, nrows, PREV[m], CUR[m], NXT[m], c0, c1, j0, kk, n1, n2, vplane, acc, tmin, tmax); \
+          }                                                                                                             \
+          stencil_refresh_thresholds(acc, tmin, tmax);                                                                  \
+        }                                                                                                               \
+        KB200_STENCIL_RELEASE(scur)                                                                                     \
       }
       int t = 1;
       for (; t + 2 <= L - 2; t += 3) {
@@ -340,11 +407,11 @@ __global__ void __launch_bounds__(CT + 32, 1) stencil7_tma_kernel(const StencilT
 #undef KB200_STENCIL_STEP
       {  // the ke halo plane is done too
         const unsigned slast = (pos + L - 1) % NS;
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty[slast]);
+        KB200_STENCIL_RELEASE(slast)
       }
       pos += (unsigned)L;
     }
+#undef KB200_STENCIL_RELEASE
   }
   __syncthreads();
   block_reduce(red, acc, red_smem);
@@ -352,12 +419,12 @@ __global__ void __launch_bounds__(CT + 32, 1) stencil7_tma_kernel(const StencilT
   grid_reduce_and_store(red, acc, scratch, red_smem);
 }
 
-template <int BJ, int NS, int CT, int N0T>
+template <int BJ, int NS, int CT, int N0T, bool PW = (CT % 128 != 0)>
 int launch_tma(b200_instance* I, const double* u, double* v_out, int n0, int n1, int n2, double c0, double c1,
                b200_minmaxloc_f64* rh, b200_minmaxloc_f64* rd) {
   const char* where = "b200_stencil7_minmaxloc_f64 (tma)";
   HostRuntime rt(I);
-  auto kern = v_out ? stencil7_tma_kernel<BJ, NS, CT, true, N0T> : stencil7_tma_kernel<BJ, NS, CT, false, N0T>;
+  auto kern = v_out ? stencil7_tma_kernel<BJ, NS, CT, true, N0T, PW> : stencil7_tma_kernel<BJ, NS, CT, false, N0T, PW>;
   const size_t smem = (size_t)NS * stencil_stage_elems(BJ, n0) * sizeof(double) + 2 * NS * sizeof(unsigned long long);
   static size_t smem_set_[2] = {0, 0};
   size_t& smem_set = smem_set_[v_out ? 1 : 0];  // grow-only opt-in, like the reference's func-attr cache (KernelLaunch.hpp:131-145)
@@ -388,8 +455,8 @@ int launch_tma(b200_instance* I, const double* u, double* v_out, int n0, int n1,
   if ((rc = rt.reduce_scratch((size_t)grid * sizeof(V), sizeof(V), rh != nullptr, &s.partials, &s.ticket, &slot_dev, &slot_host))) return rc;
   s.result0 = rh ? slot_dev : (void*)rd;
   s.result1 = rh ? (void*)rd : nullptr;
-  StencilTmaParams p{u, v_out, n0, n1, n2, kc, tiles_j, tiles_k, c0, c1};
-  kern<<<grid, CT + 32, smem, rt.stream()>>>(p, s);
+  StencilTmaParams p{u, v_out, n0, n1, n2, kc, tiles_j, tiles_k, c0, c1, b200_tune("stencil.dbg", 0)};
+  kern<<<grid, CT + (PW ? 32 : 0), smem, rt.stream()>>>(p, s);
   if ((rc = rt.check_launch(where))) return rc;
   if (rh) {
     if ((rc = rt.fence(where))) return rc;
@@ -420,9 +487,9 @@ extern "C" int b200_stencil7_minmaxloc_f64(b200_instance* I, const double* u, do
   if (ct == CT && ns == NS)                                                                                              \
     rc = n0 == 512 ? launch_tma<BJ, NS, CT, 512>(I, u, v_out, (int)n0, (int)n1, (int)n2, c0, c1, rh, rd)                 \
                    : launch_tma<BJ, NS, CT, 0>(I, u, v_out, (int)n0, (int)n1, (int)n2, c0, c1, rh, rd);
-    TMA_CFG(8, 5, 256) TMA_CFG(8, 5, 352) TMA_CFG(8, 5, 224)
+    TMA_CFG(8, 5, 512) TMA_CFG(8, 5, 352) TMA_CFG(8, 5, 224)
 #ifdef B200_SWEEP
-    TMA_CFG(8, 4, 256) TMA_CFG(8, 3, 256) TMA_CFG(8, 5, 512) TMA_CFG(8, 4, 512) TMA_CFG(8, 5, 128)
+    TMA_CFG(8, 4, 512) TMA_CFG(8, 4, 352) TMA_CFG(8, 5, 384) TMA_CFG(8, 5, 256)
 #endif
 #undef TMA_CFG
     if (rc == B200_EUNSUPPORTED) return b200_set_error(rc, where, "tuning combination not compiled in");

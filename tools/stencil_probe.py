@@ -26,9 +26,16 @@ def main():
     vout = torch.empty(n, dtype=torch.float64, device="cuda")
     vu, vv = space.wrap(u.data_ptr(), n, np.float64), space.wrap(vout.data_ptr(), n, np.float64)
     ref = None
-    cts = (224, 256, 352, 512, 128) if "--sweep" in sys.argv else (224, 256, 352)
+    if "--dbg" in sys.argv:
+        for dbg in (0, 1, 2):
+            kb.tune_set("stencil.dbg", dbg)
+            b, m = time_it(lambda: space.stencil7_minmaxloc(vu, n0, n1, n2, 0.5, 0.125), side, 10)
+            print(f"dbg={dbg} best {b:.3f} med {m:.3f} ms", flush=True)
+        kb.tune_set("stencil.dbg", 0)
+        return
+    cts = (224, 256, 352, 384, 512) if "--sweep" in sys.argv else (224, 352, 512)
     nss = (5, 4, 3) if "--sweep" in sys.argv else (5,)
-    for tma, ct, ns, kc in itertools.chain([(0, 0, 0, 0)], itertools.product((1,), cts, nss, (0, 16, 64))):
+    for tma, ct, ns, kc in itertools.chain([(0, 0, 0, 0)], itertools.product((1,), cts, nss, (0, 32))):
         kb.tune_set("stencil.tma", tma)
         if tma:
             kb.tune_set("stencil.ct", ct); kb.tune_set("stencil.ns", ns); kb.tune_set("stencil.kc", kc)
