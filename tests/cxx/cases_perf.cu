@@ -117,6 +117,45 @@ int kb200_perf_stream(int op, i64 n, int warm, int reps, double* out_ms) {
   });
 }
 
+// C3 tuning variants of the generic scan's tile shape (BLOCK x ITEMS), same lambda; variant 0 = the public parallel_scan
+int kb200_perf_scan_variant(int variant, i64 n, int warm, int reps, double* out_ms, i64* total) {
+  return guarded([&] {
+    View<i64*> x(view_alloc(WithoutInitializing, "x"), (size_t)n), y(view_alloc(WithoutInitializing, "y"), (size_t)n);
+    parallel_for("fill", n, KB200_LAMBDA(const i64 i) { x(i) = (i64)((((unsigned long long)i * 2654435761ull) >> 7) % 7) - 3; });
+    fence();
+    i64 t = 0;
+    auto f = KB200_LAMBDA(const i64 i, i64& u, const bool fin) { if (fin) y(i) = u; u += x(i); };
+    using F = decltype(f);
+    using Pol = RangePolicy<>;
+    using Red = Impl::FunctorReducer<F, i64, void>;
+    Pol pol(0, n);
+    auto run = [&](auto tag) {
+      using G = decltype(tag);
+      time_call([&] { Impl::throw_on_error(G::run(pol, f, Red{f}, &t, nullptr)); }, warm, reps, out_ms);
+    };
+    switch (variant) {
+      case 0: run(Impl::GenericScan<Pol, F, Red>{}); break;
+      case 1: run(Impl::GenericScan<Pol, F, Red, 256, 13>{}); break;
+      case 2: run(Impl::GenericScan<Pol, F, Red, 256, 17>{}); break;
+      case 3: run(Impl::GenericScan<Pol, F, Red, 512, 9>{}); break;
+      case 4: run(Impl::GenericScan<Pol, F, Red, 512, 13>{}); break;
+      case 5: run(Impl::GenericScan<Pol, F, Red, 128, 17>{}); break;
+      case 6: run(Impl::GenericScan<Pol, F, Red, 128, 9>{}); break;
+      case 7: run(Impl::GenericScan<Pol, F, Red, 1024, 9>{}); break;
+      case 8: run(Impl::GenericScan<Pol, F, Red, 256, 21>{}); break;
+      case 9: run(Impl::GenericScan<Pol, F, Red, 256, 25>{}); break;
+      case 10: run(Impl::GenericScan<Pol, F, Red, 512, 17>{}); break;
+      case 11: run(Impl::GenericScan<Pol, F, Red, 512, 21>{}); break;
+      case 12: run(Impl::GenericScan<Pol, F, Red, 1024, 13>{}); break;
+      case 13: run(Impl::GenericScan<Pol, F, Red, 1024, 17>{}); break;
+      case 14: run(Impl::GenericScan<Pol, F, Red, 128, 25>{}); break;
+      default: return -1;
+    }
+    *total = t;
+    return 0;
+  });
+}
+
 // C3: parallel_scan exclusive prefix sum, lambda form, with total
 int kb200_perf_scan(i64 n, int warm, int reps, double* out_ms, i64* total) {
   return guarded([&] {

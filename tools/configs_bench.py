@@ -50,6 +50,7 @@ def main():
     except Exception:
         pass
     rows = []
+    log2ns = tuple(int(x) for x in os.environ.get("KB200_LOG2N", "27,30").split(","))  # ncu runs use 27 only
 
     def want(tag):
         return only is None or tag in only
@@ -81,7 +82,7 @@ def main():
 
     # ------------------------------------------------------------------ C1 reduce
     if want("c1"):
-        for log2n in (27, 30):
+        for log2n in log2ns:
             n = 1 << log2n
             x = torch.empty(n, dtype=torch.float64, device=dev)
             CH = 1 << 26
@@ -127,7 +128,7 @@ def main():
 
     # ------------------------------------------------------------------ C3 scan
     if want("c3"):
-        for log2n in (27, 30):
+        for log2n in log2ns:
             n = 1 << log2n
             xi = torch.empty(n, dtype=torch.int64, device=dev)
             yi = torch.empty(n, dtype=torch.int64, device=dev)
