@@ -43,7 +43,7 @@ int run_cfg(b200_instance* I, const T* x, int64_t n, int64_t base, typename Red:
   Body body(x, (int64)n, (int64)base);
   V dummy;
   Red red(dummy);
-  return RangeReduceLaunch<Body, Red, BLOCK, UNROLL>::run(I, body, red, body.nvec, rh, rd, bps);
+  return RangeReduceLaunch<Body, Red, BLOCK, UNROLL, 1024 / BLOCK>::run(I, body, red, body.nvec, rh, rd, bps);  // <= 64 registers: see Parallel.hpp
 }
 
 // shipped configuration (see DESIGN.md "reduce kernel: tuning"); the f64 Sum path additionally

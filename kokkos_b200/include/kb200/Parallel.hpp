@@ -172,7 +172,10 @@ void reduce_dispatch(const RangePolicy<P...>& policy, const F& f, const Red& red
   Body body{f, policy.begin()};
   // wider unroll for small values: more independent loads in flight per thread
   constexpr int UNROLL = sizeof(V) <= 8 ? 8 : (sizeof(V) <= 32 ? 4 : 2);
-  throw_on_error(RangeReduceLaunch<Body, Red, 256, UNROLL>::run(policy.space().impl_instance(), body, red, n, t.host, t.dev));
+  // __launch_bounds__(256, 4): caps the kernel at 64 registers so >= 1024 threads stay resident per SM.  Without it the
+  // 32-byte MinMaxLoc kernels took 142 registers (shuffle trees of the epilogue), one CTA per SM, 12 % occupancy and
+  // 3.2 TB/s (profiles/r01_reduce_minmaxloc_ncu.txt); the hot loop itself needs < 48.
+  throw_on_error(RangeReduceLaunch<Body, Red, 256, UNROLL, 4>::run(policy.space().impl_instance(), body, red, n, t.host, t.dev));
 }
 template <class... P, class F, class Red>
 void reduce_dispatch(const MDRangePolicy<P...>& policy, const F& f, const Red& red, ResultTarget<typename Red::value_type> t) {
