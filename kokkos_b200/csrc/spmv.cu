@@ -22,35 +22,73 @@ using namespace kb200;
 using namespace kb200::Impl;
 
 namespace {
-template <int BLOCK, int VL>
+// UR consecutive rows per lane group and iteration (independent row_map / col_idx / x requests in flight).  Measured on B200
+// (profiles/r01_spmv_probe.log): UR > 1 does NOT help -- the kernel is bound by L1 wavefronts of the x gather (one 32-byte
+// sector per lane for random columns, ~1 wavefront/clk/SM => ~0.48 ms for 2^27 gathers), not by requests in flight; the
+// shipped configuration is UR = 1 and 16 lanes per row at 32 nnz/row (3.1 TB/s of algorithmic bytes).
+// Per-row arithmetic is unchanged: lane `sub` folds nonzeros sub, sub+VL, ... left to right, then a log2(VL) xor tree.
+template <int BLOCK, int VL, int UR>
 __global__ void __launch_bounds__(BLOCK) spmv_crs_kernel(int64 nrows, const int64* __restrict__ row_map,
                                                          const int* __restrict__ col_idx, const double* __restrict__ values,
                                                          const double* __restrict__ x, double* __restrict__ y) {
   const int sub = threadIdx.x % VL;
   const int64 groups_per_grid = (int64)gridDim.x * (BLOCK / VL);
-  for (int64 row = (int64)blockIdx.x * (BLOCK / VL) + threadIdx.x / VL; row < nrows; row += groups_per_grid) {
-    const int64 kb = __ldg(row_map + row), ke = __ldg(row_map + row + 1);
-    double acc = 0.0;
-    for (int64 k = kb + sub; k < ke; k += VL) acc = __dadd_rn(acc, __dmul_rn(__ldg(values + k), __ldg(x + __ldg(col_idx + k))));
+  for (int64 row0 = ((int64)blockIdx.x * (BLOCK / VL) + threadIdx.x / VL) * UR; row0 < nrows; row0 += groups_per_grid * UR) {
+    int64 kb[UR], ke[UR];
 #pragma unroll
-    for (int m = VL / 2; m > 0; m >>= 1) acc = __dadd_rn(acc, shfl_xor(acc, m));
-    if (sub == 0) y[row] = acc;
+    for (int q = 0; q < UR; ++q) {
+      const int64 r = row0 + q < nrows ? row0 + q : nrows - 1;
+      kb[q] = __ldg(row_map + r);
+      ke[q] = row0 + q < nrows ? __ldg(row_map + r + 1) : kb[q];  // rows past the end are empty
+    }
+    double acc[UR];
+    int64 longest = 0;
+#pragma unroll
+    for (int q = 0; q < UR; ++q) { acc[q] = 0.0; longest = ke[q] - kb[q] > longest ? ke[q] - kb[q] : longest; }
+    for (int64 t = sub; t < longest; t += VL) {
+      int c[UR];
+      double v[UR];
+#pragma unroll
+      for (int q = 0; q < UR; ++q) {
+        const bool in = kb[q] + t < ke[q];
+        c[q] = in ? __ldg(col_idx + kb[q] + t) : -1;
+        v[q] = in ? __ldg(values + kb[q] + t) : 0.0;
+      }
+      double xv[UR];
+#pragma unroll
+      for (int q = 0; q < UR; ++q) xv[q] = c[q] >= 0 ? __ldg(x + c[q]) : 0.0;
+#pragma unroll
+      for (int q = 0; q < UR; ++q)
+        if (c[q] >= 0) acc[q] = __dadd_rn(acc[q], __dmul_rn(v[q], xv[q]));
+    }
+#pragma unroll
+    for (int q = 0; q < UR; ++q) {
+#pragma unroll
+      for (int m = VL / 2; m > 0; m >>= 1) acc[q] = __dadd_rn(acc[q], shfl_xor(acc[q], m));
+    }
+    if (sub < UR && row0 + sub < nrows) {
+      double out = acc[0];
+#pragma unroll
+      for (int q = 1; q < UR; ++q) out = sub == q ? acc[q] : out;
+      y[row0 + sub] = out;  // UR consecutive rows written by UR lanes: one coalesced store
+    }
   }
 }
 
-template <int VL>
+template <int VL, int UR>
 int launch(b200_instance* I, int64 nrows, const int64* row_map, const int* col_idx, const double* values, const double* x, double* y) {
   constexpr int BLOCK = 256;
   HostRuntime rt(I);
   static int bps = 0;
   if (!bps) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, spmv_crs_kernel<BLOCK, VL>, BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, spmv_crs_kernel<BLOCK, VL, UR>, BLOCK, 0);
     if (bps < 1) bps = 1;
   }
-  int64 blocks = (nrows + BLOCK / VL - 1) / (BLOCK / VL);
+  const int64 rows_per_block = (int64)(BLOCK / VL) * UR;
+  int64 blocks = (nrows + rows_per_block - 1) / rows_per_block;
   const int64 max_grid = (int64)rt.sm_count() * bps * 4;  // a few waves: rows differ in length
   const int grid = (int)(blocks < max_grid ? blocks : max_grid);
-  spmv_crs_kernel<BLOCK, VL><<<grid, BLOCK, 0, rt.stream()>>>(nrows, row_map, col_idx, values, x, y);
+  spmv_crs_kernel<BLOCK, VL, UR><<<grid, BLOCK, 0, rt.stream()>>>(nrows, row_map, col_idx, values, x, y);
   return rt.check_launch("b200_spmv_crs_f64");
 }
 }  // namespace
@@ -74,14 +112,15 @@ extern "C" int b200_spmv_crs_f64(b200_instance* I, int64_t nrows, const int64_t*
   int vl = b200_tune("spmv.vl", 0);
   if (vl == 0) {
     const double mean = (double)nnz / (double)nrows;
-    vl = mean <= 6 ? 4 : mean <= 12 ? 8 : mean <= 24 ? 16 : 32;
+    vl = mean <= 6 ? 4 : mean <= 12 ? 8 : mean <= 64 ? 16 : 32;  // B200 probe (profiles/r01_spmv_probe.log): 16 lanes beat 32 at 32 nnz/row
   }
   const int64* rm = (const int64*)row_map;
-  switch (vl) {
-    case 4: return launch<4>(I, nrows, rm, col_idx, values, x, y);
-    case 8: return launch<8>(I, nrows, rm, col_idx, values, x, y);
-    case 16: return launch<16>(I, nrows, rm, col_idx, values, x, y);
-    case 32: return launch<32>(I, nrows, rm, col_idx, values, x, y);
-  }
-  return b200_set_error(B200_EUNSUPPORTED, where, "vector length must be 4, 8, 16 or 32");
+  const int ur = b200_tune("spmv.ur", 1);
+#define SPMV_CFG(VL, UR) if (vl == VL && ur == UR) return launch<VL, UR>(I, nrows, rm, col_idx, values, x, y);
+  SPMV_CFG(4, 1) SPMV_CFG(8, 1) SPMV_CFG(16, 1) SPMV_CFG(32, 1)
+#ifdef B200_SWEEP
+  SPMV_CFG(4, 4) SPMV_CFG(8, 4) SPMV_CFG(16, 4) SPMV_CFG(32, 4) SPMV_CFG(32, 2) SPMV_CFG(32, 8) SPMV_CFG(16, 2) SPMV_CFG(16, 8) SPMV_CFG(8, 8) SPMV_CFG(8, 2)
+#endif
+#undef SPMV_CFG
+  return b200_set_error(B200_EUNSUPPORTED, where, "vector length must be 4, 8, 16 or 32 (and spmv.ur 4)");
 }
