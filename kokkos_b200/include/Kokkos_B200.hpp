@@ -16,6 +16,7 @@
 #include "kb200/Atomic.hpp"
 #include "kb200/Parallel.hpp"
 #include "kb200/Team.hpp"
+#include "kb200/StdAlgorithms.hpp"
 
 #ifdef KB200_AS_KOKKOS
 namespace Kokkos = kb200;

@@ -1,7 +1,8 @@
 // kb200/Reducers.hpp -- the built-in reducers of the hot path, same names and semantics as
 // core/src/Kokkos_Parallel_Reduce.hpp:33-1352 and identities as core/src/Kokkos_ReductionIdentity.hpp.
 //
-//   Sum, Prod, Min, Max, LAnd, LOr, BAnd, BOr, MinLoc, MaxLoc, MinMax, MinMaxLoc
+//   Sum, Prod, Min, Max, LAnd, LOr, BAnd, BOr, MinLoc, MaxLoc, MinMax, MinMaxLoc,
+//   MinFirstLoc, MaxFirstLoc, MinMaxFirstLastLoc, FirstLoc, LastLoc
 //   ValLocScalar, MinMaxScalar, MinMaxLocScalar, reduction_identity<T>
 //
 // A reducer is constructed from a scalar reference (blocking, result on return) or from anything
@@ -219,6 +220,79 @@ struct MinMaxLoc : Impl::ReducerBase<MinMaxLocScalar<std::remove_cv_t<Scalar>, s
     v.min_loc = reduction_identity<index_type>::min();
   }
 };
+
+// ---- first/last-location reducers used by the std-algorithm layer (core/src/Kokkos_Parallel_Reduce.hpp:679-1228):
+//      MaxFirstLoc / MinFirstLoc keep the LOWEST location among equal extrema, MinMaxFirstLastLoc the lowest location of the
+//      minimum and the HIGHEST location of the maximum (std::minmax_element), FirstLoc / LastLoc the lowest / highest
+//      location at which a predicate held.  All joins are commutative.
+template <class Scalar, class Index, class Space = HostSpace>
+struct MaxFirstLoc : Impl::ReducerBase<ValLocScalar<std::remove_cv_t<Scalar>, std::remove_cv_t<Index>>> {
+  using scalar_type = std::remove_cv_t<Scalar>;
+  using index_type = std::remove_cv_t<Index>;
+  KB200_REDUCER_HEAD(MaxFirstLoc, ValLocScalar<scalar_type, index_type>)
+  KB200_FORCEINLINE_FUNCTION void join(value_type& dest, const value_type& src) const {
+    if (dest.val < src.val) dest = src;
+    else if (!(src.val < dest.val) && src.loc < dest.loc) dest.loc = src.loc;
+  }
+  KB200_FORCEINLINE_FUNCTION void init(value_type& v) const {
+    v.val = reduction_identity<scalar_type>::max();
+    v.loc = reduction_identity<index_type>::min();
+  }
+};
+template <class Scalar, class Index, class Space = HostSpace>
+struct MinFirstLoc : Impl::ReducerBase<ValLocScalar<std::remove_cv_t<Scalar>, std::remove_cv_t<Index>>> {
+  using scalar_type = std::remove_cv_t<Scalar>;
+  using index_type = std::remove_cv_t<Index>;
+  KB200_REDUCER_HEAD(MinFirstLoc, ValLocScalar<scalar_type, index_type>)
+  KB200_FORCEINLINE_FUNCTION void join(value_type& dest, const value_type& src) const {
+    if (src.val < dest.val) dest = src;
+    else if (!(dest.val < src.val) && src.loc < dest.loc) dest.loc = src.loc;
+  }
+  KB200_FORCEINLINE_FUNCTION void init(value_type& v) const {
+    v.val = reduction_identity<scalar_type>::min();
+    v.loc = reduction_identity<index_type>::min();
+  }
+};
+template <class Scalar, class Index, class Space = HostSpace>
+struct MinMaxFirstLastLoc : Impl::ReducerBase<MinMaxLocScalar<std::remove_cv_t<Scalar>, std::remove_cv_t<Index>>> {
+  using scalar_type = std::remove_cv_t<Scalar>;
+  using index_type = std::remove_cv_t<Index>;
+  KB200_REDUCER_HEAD(MinMaxFirstLastLoc, MinMaxLocScalar<scalar_type, index_type>)
+  KB200_FORCEINLINE_FUNCTION void join(value_type& dest, const value_type& src) const {
+    if (src.min_val < dest.min_val) { dest.min_val = src.min_val; dest.min_loc = src.min_loc; }
+    else if (!(dest.min_val < src.min_val) && src.min_loc < dest.min_loc) dest.min_loc = src.min_loc;
+    if (dest.max_val < src.max_val) { dest.max_val = src.max_val; dest.max_loc = src.max_loc; }
+    else if (!(src.max_val < dest.max_val) && src.max_loc > dest.max_loc) dest.max_loc = src.max_loc;
+  }
+  KB200_FORCEINLINE_FUNCTION void init(value_type& v) const {
+    v.max_val = reduction_identity<scalar_type>::max();
+    v.min_val = reduction_identity<scalar_type>::min();
+    v.max_loc = reduction_identity<index_type>::max();
+    v.min_loc = reduction_identity<index_type>::min();
+  }
+};
+template <class Index>
+struct FirstLocScalar { Index min_loc_true; };
+template <class Index>
+struct LastLocScalar { Index max_loc_true; };
+template <class Index, class Space = HostSpace>
+struct FirstLoc : Impl::ReducerBase<FirstLocScalar<std::remove_cv_t<Index>>> {
+  using index_type = std::remove_cv_t<Index>;
+  KB200_REDUCER_HEAD(FirstLoc, FirstLocScalar<index_type>)
+  KB200_FORCEINLINE_FUNCTION void join(value_type& dest, const value_type& src) const {
+    if (src.min_loc_true < dest.min_loc_true) dest.min_loc_true = src.min_loc_true;
+  }
+  KB200_FORCEINLINE_FUNCTION void init(value_type& v) const { v.min_loc_true = reduction_identity<index_type>::min(); }
+};
+template <class Index, class Space = HostSpace>
+struct LastLoc : Impl::ReducerBase<LastLocScalar<std::remove_cv_t<Index>>> {
+  using index_type = std::remove_cv_t<Index>;
+  KB200_REDUCER_HEAD(LastLoc, LastLocScalar<index_type>)
+  KB200_FORCEINLINE_FUNCTION void join(value_type& dest, const value_type& src) const {
+    if (src.max_loc_true > dest.max_loc_true) dest.max_loc_true = src.max_loc_true;
+  }
+  KB200_FORCEINLINE_FUNCTION void init(value_type& v) const { v.max_loc_true = reduction_identity<index_type>::max(); }
+};
 #undef KB200_REDUCER_HEAD
 
 template <class T>
@@ -235,6 +309,11 @@ template <class S, class I, class Sp> struct is_reducer<MinLoc<S, I, Sp>> : std:
 template <class S, class I, class Sp> struct is_reducer<MaxLoc<S, I, Sp>> : std::true_type {};
 template <class S, class Sp> struct is_reducer<MinMax<S, Sp>> : std::true_type {};
 template <class S, class I, class Sp> struct is_reducer<MinMaxLoc<S, I, Sp>> : std::true_type {};
+template <class S, class I, class Sp> struct is_reducer<MaxFirstLoc<S, I, Sp>> : std::true_type {};
+template <class S, class I, class Sp> struct is_reducer<MinFirstLoc<S, I, Sp>> : std::true_type {};
+template <class S, class I, class Sp> struct is_reducer<MinMaxFirstLastLoc<S, I, Sp>> : std::true_type {};
+template <class I, class Sp> struct is_reducer<FirstLoc<I, Sp>> : std::true_type {};
+template <class I, class Sp> struct is_reducer<LastLoc<I, Sp>> : std::true_type {};
 // user-defined reducers: anything that names itself in a nested `reducer` typedef
 // (the reference's detection: Kokkos_Parallel_Reduce.hpp is_reducer via T::reducer)
 template <class T, class = void>

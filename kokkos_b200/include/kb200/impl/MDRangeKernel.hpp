@@ -9,6 +9,9 @@
 // (SMs x resident blocks) strides over the tiles; the tile coordinates advance by a pre-decomposed stride
 // with carries (adds and compares only).  The reference's reduce variant instead launches <= 512 blocks
 // with tile_prod of 256 threads active and pays a div/mod per rank per element.
+// Thread coarsening: when the slowest dimension is long enough each thread handles C = 4 CONSECUTIVE indices of it per tile
+// visit (a tile visit then covers tile[R-1]*C indices there), so the tile bookkeeping (carry chain, bounds tests, index
+// construction) is paid once per 4 points and the compiler can reuse loads between neighbouring points of a stencil.
 // Reductions reuse the block/grid combine of Collectives.hpp (ordered, ticketed, result to a pinned slot).
 #ifndef KB200_IMPL_MDRANGEKERNEL_HPP
 #define KB200_IMPL_MDRANGEKERNEL_HPP
@@ -34,7 +37,7 @@ KB200_DEVICE_FUNCTION void md_invoke(const F& f, const Index* idx, std::index_se
 }
 
 // walks the tiles owned by this block; calls op(idx) for every in-range point handled by this thread
-template <int RANK, class Index, class Op>
+template <int RANK, int C, class Index, class Op>
 KB200_DEVICE_FUNCTION void md_walk(const MDParams<RANK, Index>& p, Op op) {
   // this thread's fixed offset inside any tile
   Index off[RANK];
@@ -56,11 +59,18 @@ KB200_DEVICE_FUNCTION void md_walk(const MDParams<RANK, Index>& p, Op op) {
     Index idx[RANK];
     bool in = true;
 #pragma unroll
-    for (int d = 0; d < RANK; ++d) {
+    for (int d = 0; d < RANK - 1; ++d) {
       idx[d] = p.lower[d] + t[d] * p.tile[d] + off[d];
       in = in && (idx[d] < p.upper[d]);
     }
-    if (in) op(idx);
+    const Index last0 = p.lower[RANK - 1] + (t[RANK - 1] * p.tile[RANK - 1] + off[RANK - 1]) * (Index)C;
+    if (in) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        idx[RANK - 1] = last0 + (Index)c;
+        if (idx[RANK - 1] < p.upper[RANK - 1]) op(idx);
+      }
+    }
     // advance by the grid stride: mixed-radix add with carry
     Index carry = 0;
 #pragma unroll
@@ -72,19 +82,19 @@ KB200_DEVICE_FUNCTION void md_walk(const MDParams<RANK, Index>& p, Op op) {
   }
 }
 
-template <class F, class Tag, int RANK, class Index>
+template <class F, class Tag, int RANK, class Index, int C>
 __global__ void mdrange_for_kernel(const __grid_constant__ F f, const __grid_constant__ MDParams<RANK, Index> p) {
-  md_walk<RANK, Index>(p, [&](const Index* idx) { md_invoke<Tag>(f, idx, std::make_index_sequence<RANK>{}); });
+  md_walk<RANK, C, Index>(p, [&](const Index* idx) { md_invoke<Tag>(f, idx, std::make_index_sequence<RANK>{}); });
 }
 
-template <class F, class Tag, class Red, int RANK, class Index>
+template <class F, class Tag, class Red, int RANK, class Index, int C>
 __global__ void mdrange_reduce_kernel(const __grid_constant__ F f, const __grid_constant__ Red red,
                                       const __grid_constant__ MDParams<RANK, Index> p, const ReduceScratch scratch) {
   using V = typename Red::value_type;
   __shared__ __align__(16) unsigned char smem[32 * sizeof(V)];
   V acc;
   red.init(acc);
-  md_walk<RANK, Index>(p, [&](const Index* idx) { md_invoke<Tag>(f, idx, std::make_index_sequence<RANK>{}, acc); });
+  md_walk<RANK, C, Index>(p, [&](const Index* idx) { md_invoke<Tag>(f, idx, std::make_index_sequence<RANK>{}, acc); });
   block_reduce(red, acc, smem);
   __syncthreads();
   grid_reduce_and_store(red, acc, scratch, smem);
@@ -97,6 +107,19 @@ struct MDLaunchShape {
   MDParams<RANK, Index> p;
   dim3 block;
   int threads;
+  int coarsen = 1;
+  static constexpr int kCoarsen = 4;
+  // coarsen the slowest dimension by kCoarsen if that still leaves >= 8 tile visits per SM-resident block slot
+  void maybe_coarsen(int sm_count) {
+    const long long e = (long long)p.tile_end[RANK - 1];
+    if (e < 2 * kCoarsen) return;
+    const long long e2 = (e + kCoarsen - 1) / kCoarsen;
+    const long long nt2 = p.num_tiles / e * e2;
+    if (nt2 < (long long)sm_count * 64) return;
+    p.tile_end[RANK - 1] = (Index)e2;
+    p.num_tiles = nt2;
+    coarsen = kCoarsen;
+  }
   explicit MDLaunchShape(const Policy& pol) {
     long long z = 1;
     for (int d = 0; d < RANK; ++d) {
@@ -127,7 +150,8 @@ struct MDRangeFor {
     using Tag = typename Policy::work_tag;
     MDLaunchShape<Policy> sh(pol);
     HostRuntime rt(pol.space().impl_instance());
-    auto k = mdrange_for_kernel<F, Tag, RANK, Index>;
+    sh.maybe_coarsen(rt.sm_count());
+    auto k = sh.coarsen > 1 ? mdrange_for_kernel<F, Tag, RANK, Index, MDLaunchShape<Policy>::kCoarsen> : mdrange_for_kernel<F, Tag, RANK, Index, 1>;
     int bps = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, sh.threads, 0);
     if (bps < 1) bps = 1;
@@ -148,7 +172,8 @@ struct MDRangeReduce {
     using Tag = typename Policy::work_tag;
     MDLaunchShape<Policy> sh(pol);
     HostRuntime rt(pol.space().impl_instance());
-    auto k = mdrange_reduce_kernel<F, Tag, Red, RANK, Index>;
+    sh.maybe_coarsen(rt.sm_count());
+    auto k = sh.coarsen > 1 ? mdrange_reduce_kernel<F, Tag, Red, RANK, Index, MDLaunchShape<Policy>::kCoarsen> : mdrange_reduce_kernel<F, Tag, Red, RANK, Index, 1>;
     int bps = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, sh.threads, 0);
     if (bps < 1) bps = 1;

@@ -161,6 +161,8 @@ def test_mdrange_stencil_minmaxloc_lambda(cases, port, dims):
     (3, (1, -2, 3), (40, 11, 20), (16, 2, 4)), (4, (0, 0, 0, 0), (9, 8, 7, 6), None), (4, (0, 1, 2, 3), (12, 9, 8, 7), (4, 2, 2, 3)),
     (5, (0, 0, 0, 0, 0), (7, 6, 5, 4, 3), None), (6, (0, 0, 0, 0, 0, 0), (5, 4, 3, 4, 3, 2), (4, 2, 2, 2, 1, 2)),
     (3, (0, 0, 0), (0, 5, 5), None),                      # zero-length dimension: nothing runs, reduce = 0
+    # large enough for the thread-coarsened kernels (4 consecutive slowest-dimension indices per thread), ragged ends
+    (2, (-7, 3), (1990, 3002), None), (3, (-3, 2, -5), (125, 66, 1994), None), (3, (0, 0, 0), (64, 33, 2001), (32, 2, 1)),
 ])
 def test_mdrange_every_point_exactly_once(cases, rank, lower, upper, tile):
     ext = [u - l for l, u in zip(lower, upper)]
