@@ -102,6 +102,13 @@ int b200_scan_begin(b200_instance* inst, uint64_t ntiles, uint64_t* epoch, uint6
  * and (if want_result_slot) a fresh pinned+mapped result slot of >= value_bytes from a 64-entry ring */
 int b200_reduce_scratch(b200_instance* inst, size_t partial_bytes, size_t value_bytes, int want_result_slot,
                         void** partials_dev, unsigned** ticket_dev, void** slot_dev, void** slot_host);
+/* low-latency scalar hand-back: a result slot plus a completion sequence word that the kernel writes (after a system-scope
+ * fence) when the value is in place; b200_result_wait polls it instead of synchronising the stream (it still surfaces
+ * launch failures through periodic cudaStreamQuery).  Replaces the fence + copy of
+ * core/src/Cuda/Kokkos_Cuda_Parallel_Range.hpp:344-360. */
+int b200_result_slot(b200_instance* inst, size_t value_bytes, void** slot_dev, void** slot_host, unsigned long long** seq_dev,
+                     unsigned long long* seq_value);
+int b200_result_wait(b200_instance* inst, const void* slot_host, unsigned long long seq_value, const char* label);
 int b200_instance_sm_count(b200_instance* inst);
 /* record a CUDA error code raised in the header-only layer; returns the code (0 stays 0) */
 int b200_report_error(int code, const char* where);

@@ -94,6 +94,8 @@ def load_library() -> ctypes.CDLL:
         "b200_spmv_crs_f64": [P, c_int64, P, P, P, P, P],
         "b200_scan_excl_i64_seed_dev": [P, P, P, c_int64, P, P],
         "b200_scan_excl_i64_seeds_dev": [P, P, P, c_int64, P, c_int, P],
+        "b200_result_slot": [P, c_size_t, POINTER(P), POINTER(P), POINTER(P), POINTER(c_uint64)],
+        "b200_result_wait": [P, P, c_uint64, c_char_p],
         "b200_reduce_sum_f64_host": [P, P, c_int64, P],
         "b200_scan_excl_i64_host": [P, P, P, c_int64, c_int64, P],
     }

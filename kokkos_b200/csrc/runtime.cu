@@ -111,8 +111,8 @@ static int instance_setup(int device, cudaStream_t stream, bool owns_stream, b20
   if ((e = cudaMalloc(&I->partials, I->partials_bytes)) != cudaSuccess) return fail(e, "partials");
   if ((e = cudaMalloc((void**)&I->flags, 256)) != cudaSuccess) return fail(e, "flags");
   if ((e = cudaMemsetAsync(I->flags, 0, 256, I->stream)) != cudaSuccess) return fail(e, "flags memset");
-  I->slot_bytes = 256;
-  if ((e = cudaHostAlloc(&I->result_ring, (size_t)kResultSlots * I->slot_bytes, cudaHostAllocMapped)) != cudaSuccess)
+  I->slot_bytes = 256;  // value bytes; each slot is followed by a 64-byte trailer whose first word is the completion sequence
+  if ((e = cudaHostAlloc(&I->result_ring, (size_t)kResultSlots * (I->slot_bytes + kSlotTrailer), cudaHostAllocMapped)) != cudaSuccess)
     return fail(e, "pinned result ring");
   if ((e = cudaHostGetDevicePointer(&I->result_ring_dev, I->result_ring, 0)) != cudaSuccess) return fail(e, "map ring");
   I->scan_desc_bytes = (size_t)32 << 20;
@@ -271,8 +271,8 @@ int b200_scratch_get(b200_instance* I, int kind, size_t bytes, void** dev_ptr, v
     case B200_SCRATCH_RESULT: {
       if (bytes > I->slot_bytes) return b200_set_error(B200_EUNSUPPORTED, "b200_scratch_get(result)", "value larger than a result slot");
       unsigned k = I->next_slot++ % kResultSlots;
-      *dev_ptr = (char*)I->result_ring_dev + (size_t)k * I->slot_bytes;
-      if (host_ptr) *host_ptr = (char*)I->result_ring + (size_t)k * I->slot_bytes;
+      *dev_ptr = (char*)I->result_ring_dev + (size_t)k * (I->slot_bytes + kSlotTrailer);
+      if (host_ptr) *host_ptr = (char*)I->result_ring + (size_t)k * (I->slot_bytes + kSlotTrailer);
       return 0;
     }
     case B200_SCRATCH_FUNCTOR:
@@ -315,9 +315,45 @@ int b200_reduce_scratch(b200_instance* I, size_t partial_bytes, size_t value_byt
     if (value_bytes > I->slot_bytes)
       return b200_set_error(B200_EUNSUPPORTED, "b200_reduce_scratch", "reduction value larger than 256 bytes needs a device result");
     unsigned k = I->next_slot++ % kResultSlots;
-    *slot_dev = (char*)I->result_ring_dev + (size_t)k * I->slot_bytes;
-    *slot_host = (char*)I->result_ring + (size_t)k * I->slot_bytes;
+    *slot_dev = (char*)I->result_ring_dev + (size_t)k * (I->slot_bytes + kSlotTrailer);
+    *slot_host = (char*)I->result_ring + (size_t)k * (I->slot_bytes + kSlotTrailer);
   }
+  return 0;
+}
+
+int b200_result_slot(b200_instance* I, size_t value_bytes, void** slot_dev, void** slot_host, unsigned long long** seq_dev,
+                     unsigned long long* seq_value) {
+  if (!I) return b200_set_error(B200_ENOTINIT, "b200_result_slot", nullptr);
+  if (!slot_dev || !slot_host || !seq_dev || !seq_value) return b200_set_error(B200_EINVAL, "b200_result_slot", "NULL out pointer");
+  if (value_bytes > I->slot_bytes)
+    return b200_set_error(B200_EUNSUPPORTED, "b200_result_slot", "reduction value larger than 256 bytes needs a device result");
+  const unsigned long long c = I->result_seq++;  // 64-bit, never wraps in practice; value c+1 is unique per hand-out
+  const unsigned k = (unsigned)(c % kResultSlots);
+  const size_t off = (size_t)k * (I->slot_bytes + kSlotTrailer);
+  *slot_dev = (char*)I->result_ring_dev + off;
+  *slot_host = (char*)I->result_ring + off;
+  *seq_dev = (unsigned long long*)((char*)I->result_ring_dev + off + I->slot_bytes);
+  *seq_value = c + 1;
+  return 0;
+}
+
+int b200_result_wait(b200_instance* I, const void* slot_host, unsigned long long seq_value, const char* label) {
+  if (!I) return b200_set_error(B200_ENOTINIT, "b200_result_wait", nullptr);
+  const volatile unsigned long long* seq = (const volatile unsigned long long*)((const char*)slot_host + I->slot_bytes);
+  // The kernel's last block stores the value, __threadfence_system(), then the sequence word: poll it instead of paying
+  // a driver stream synchronisation.  Every 2048 polls the stream is queried so a failed launch cannot hang the host.
+  for (unsigned spin = 1;; ++spin) {
+    if (*seq == seq_value) break;
+    if ((spin & 2047u) == 0) {
+      cudaError_t e = cudaStreamQuery(I->stream);
+      if (e == cudaSuccess) {
+        if (*seq == seq_value) break;
+        return b200_set_error(B200_EINVAL, label ? label : "b200_result_wait", "stream drained but the result slot was not written");
+      }
+      if (e != cudaErrorNotReady) return b200_set_error((int)e, label ? label : "b200_result_wait", "cudaStreamQuery");
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
   return 0;
 }
 

@@ -9,6 +9,7 @@
 #include <mutex>
 
 constexpr unsigned kResultSlots = 64;
+constexpr size_t kSlotTrailer = 64;  // bytes after each result slot; word 0 = completion sequence
 
 struct b200_instance {
   int device = 0;
@@ -26,6 +27,7 @@ struct b200_instance {
   void* result_ring_dev = nullptr;  // same memory, device address
   size_t slot_bytes = 0;
   std::atomic<unsigned> next_slot{0};
+  std::atomic<unsigned long long> result_seq{0};
 
   // scan scratch
   void* scan_desc = nullptr;

@@ -139,11 +139,19 @@ KB200_DEVICE_FUNCTION V load_cg(const V* p) {
 
 // ---- inter-block combine -----------------------------------------------------------------
 struct ReduceScratch {
-  void* partials;      // >= gridDim.x * sizeof(value_type), device
-  unsigned* ticket;    // zero before the launch; reset by the last block
-  void* result0;       // device-accessible destination (pinned mapped slot or device memory), may be null
-  void* result1;       // second destination, may be null
+  void* partials = nullptr;      // >= gridDim.x * sizeof(value_type), device
+  unsigned* ticket = nullptr;    // zero before the launch; reset by the last block
+  void* result0 = nullptr;       // device-accessible destination (pinned mapped slot or device memory), may be null
+  void* result1 = nullptr;       // second destination, may be null
+  unsigned long long* seq_ptr = nullptr;  // if set: completion word in mapped host memory, written after the result
+  unsigned long long seq_val = 0;         // (system-scope fence in between) so the host can poll instead of synchronising
 };
+KB200_DEVICE_FUNCTION void reduce_signal_host(const ReduceScratch& s) {
+  if (s.seq_ptr) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(s.seq_ptr) = s.seq_val;
+  }
+}
 
 // All threads of every block must call this (it contains barriers).  `v` is meaningful in
 // thread 0 (the block's partial).  Red additionally provides init(value_type&) and
@@ -164,6 +172,7 @@ KB200_DEVICE_FUNCTION void grid_reduce_and_store(const Red& red, typename Red::v
       red.final(v);
       if (s.result0) *reinterpret_cast<V*>(s.result0) = v;
       if (s.result1) *reinterpret_cast<V*>(s.result1) = v;
+      reduce_signal_host(s);
     }
     return;
   }
@@ -192,6 +201,7 @@ KB200_DEVICE_FUNCTION void grid_reduce_and_store(const Red& red, typename Red::v
     if (s.result0) *reinterpret_cast<V*>(s.result0) = acc;
     if (s.result1) *reinterpret_cast<V*>(s.result1) = acc;
     *s.ticket = 0u;  // self-reset: stream order makes this safe for the next launch
+    reduce_signal_host(s);
   }
 }
 

@@ -20,6 +20,12 @@ struct HostRuntime {
                      void** slot_dev, void** slot_host) const {
     return b200_reduce_scratch(inst, partial_bytes, value_bytes, want_slot ? 1 : 0, partials, ticket, slot_dev, slot_host);
   }
+  int result_slot(size_t value_bytes, void** slot_dev, void** slot_host, unsigned long long** seq_dev, unsigned long long* seq_value) const {
+    return b200_result_slot(inst, value_bytes, slot_dev, slot_host, seq_dev, seq_value);
+  }
+  int result_wait(const void* slot_host, unsigned long long seq_value, const char* label) const {
+    return b200_result_wait(inst, slot_host, seq_value, label);
+  }
   int check_launch(const char* where) const { return b200_report_error((int)cudaGetLastError(), where); }
   int fence(const char* label) const { return b200_fence(inst, label); }
 };

@@ -7,8 +7,8 @@
 //     "units"; all UNROLL loads of a thread are issued before the first is consumed, so each
 //     thread keeps UNROLL independent (up to 32-byte) requests in flight;
 //   * partials never touch shared memory until the single cross-warp hop (Collectives.hpp);
-//   * the result goes straight to a pinned, device-mapped host slot: the host needs one stream
-//     sync and no memcpy (the reference: unified scratch + fence + copy, :344-360).
+//   * the result goes straight to a pinned, device-mapped host slot followed by a completion word; the host polls
+//     that word: no stream synchronisation and no memcpy (the reference: unified scratch + fence + copy, :344-360).
 //
 // Body concept (device side):
 //   using packet = ...;                                  // what load() returns (may be empty)
@@ -90,15 +90,15 @@ struct RangeReduceLaunch {
     void* slot_dev = nullptr;
     void* slot_host = nullptr;
     int rc;
-    if ((rc = rt.reduce_scratch((size_t)grid * sizeof(V), sizeof(V), result_host != nullptr, &s.partials, &s.ticket,
-                                &slot_dev, &slot_host)))
-      return rc;
+    if ((rc = rt.reduce_scratch((size_t)grid * sizeof(V), sizeof(V), false, &s.partials, &s.ticket, nullptr, nullptr))) return rc;
+    // scalar result: pinned slot + completion word polled by the host (no stream synchronisation on this path)
+    if (result_host && (rc = rt.result_slot(sizeof(V), &slot_dev, &slot_host, &s.seq_ptr, &s.seq_val))) return rc;
     s.result0 = result_host ? slot_dev : (void*)result_dev;
     s.result1 = result_host ? (void*)result_dev : nullptr;
     range_reduce_kernel<Body, Red, BLOCK, UNROLL, MIN_BLOCKS><<<grid, BLOCK, 0, rt.stream()>>>(body, red, n_units, s);
     if ((rc = rt.check_launch("kb200::range_reduce_kernel"))) return rc;
     if (result_host) {
-      if ((rc = rt.fence("kb200::parallel_reduce: fence to hand the scalar result to the host"))) return rc;
+      if ((rc = rt.result_wait(slot_host, s.seq_val, "kb200::parallel_reduce: wait for the scalar result"))) return rc;
       memcpy(result_host, slot_host, sizeof(V));
     }
     return 0;
