@@ -17,6 +17,7 @@
 #include "kb200/Parallel.hpp"
 #include "kb200/Team.hpp"
 #include "kb200/StdAlgorithms.hpp"
+#include "kb200/Compat.hpp"
 
 #ifdef KB200_AS_KOKKOS
 namespace Kokkos = kb200;

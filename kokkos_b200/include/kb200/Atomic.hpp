@@ -360,5 +360,29 @@ KB200_FORCEINLINE_FUNCTION void atomic_store(T* p, std::common_type_t<T> v) {
   KB200_ATOMIC_DISPATCH(Impl::dev::atomic_store(p, v);, __atomic_store(p, &v, __ATOMIC_RELAXED);)
 }
 
+
+// ---- element proxy of atomic Views: View<T*, MemoryTraits<Atomic>>::operator() returns this (core/src/impl/Kokkos_Atomic_View.hpp:
+//      AtomicDataElement); every operator is one atomic operation on the referenced element.
+template <class T>
+struct AtomicDataElement {
+  using value_type = std::remove_const_t<T>;
+  value_type* ptr;
+  KB200_FORCEINLINE_FUNCTION explicit AtomicDataElement(T* p) : ptr(const_cast<value_type*>(p)) {}
+  KB200_FORCEINLINE_FUNCTION operator value_type() const { return atomic_load(ptr); }
+  KB200_FORCEINLINE_FUNCTION value_type operator=(const value_type& v) const { atomic_store(ptr, v); return v; }
+  KB200_FORCEINLINE_FUNCTION value_type operator=(const AtomicDataElement& o) const { const value_type v = o; atomic_store(ptr, v); return v; }
+  KB200_FORCEINLINE_FUNCTION void operator+=(const value_type& v) const { atomic_add(ptr, v); }
+  KB200_FORCEINLINE_FUNCTION void operator-=(const value_type& v) const { atomic_sub(ptr, v); }
+  KB200_FORCEINLINE_FUNCTION void operator*=(const value_type& v) const { atomic_mul(ptr, v); }
+  KB200_FORCEINLINE_FUNCTION void operator/=(const value_type& v) const { atomic_div(ptr, v); }
+  KB200_FORCEINLINE_FUNCTION void operator&=(const value_type& v) const { atomic_and(ptr, v); }
+  KB200_FORCEINLINE_FUNCTION void operator|=(const value_type& v) const { atomic_or(ptr, v); }
+  KB200_FORCEINLINE_FUNCTION void operator^=(const value_type& v) const { atomic_xor(ptr, v); }
+  KB200_FORCEINLINE_FUNCTION value_type operator++() const { return atomic_fetch_add(ptr, value_type(1)) + value_type(1); }
+  KB200_FORCEINLINE_FUNCTION value_type operator--() const { return atomic_fetch_sub(ptr, value_type(1)) - value_type(1); }
+  KB200_FORCEINLINE_FUNCTION value_type operator++(int) const { return atomic_fetch_add(ptr, value_type(1)); }
+  KB200_FORCEINLINE_FUNCTION value_type operator--(int) const { return atomic_fetch_sub(ptr, value_type(1)); }
+};
+
 }  // namespace kb200
 #endif

@@ -58,6 +58,12 @@ inline std::shared_ptr<b200_instance>& default_instance() {
 }  // namespace Impl
 
 struct B200Space;     // device memory (View.hpp)
+template <class ExecSpace, class MemSpace>
+struct Device {  // core/src/Kokkos_Core_fwd.hpp: execution space + memory space pair
+  using execution_space = ExecSpace;
+  using memory_space = MemSpace;
+  using device_type = Device<ExecSpace, MemSpace>;
+};
 struct LayoutLeft;
 template <class ExecSpace> class ScratchMemorySpace;
 
@@ -71,6 +77,7 @@ class B200 {
  public:
   using execution_space = B200;
   using memory_space = B200Space;
+  using device_type = Device<B200, B200Space>;
   using array_layout = LayoutLeft;
   using size_type = unsigned int;
   using scratch_memory_space = ScratchMemorySpace<B200>;

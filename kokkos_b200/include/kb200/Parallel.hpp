@@ -245,7 +245,15 @@ struct scan_arg_of {
   template <class C, class R, class A0, class A1, class A2> static A1 pick(R (C::*)(A0, A1, A2));
   using type = decltype(pick(&L::operator()));
 };
-template <class F, class = void> struct scan_value_type_of {};
+// value type of a scan functor used without a total: F::value_type if published, else deduced from the (non-template)
+// call operator's second parameter, as the reference's FunctorAnalysis does (impl/Kokkos_FunctorAnalysis.hpp:77-160)
+template <class F>
+struct scan_op_value {
+  template <class C, class R, class A0, class A1, class A2> static std::remove_reference_t<A1> pick(R (C::*)(A0, A1, A2) const);
+  template <class C, class R, class T, class A0, class A1, class A2> static std::remove_reference_t<A1> pick(R (C::*)(T, A0, A1, A2) const);
+  using type = decltype(pick(&F::operator()));
+};
+template <class F, class = void> struct scan_value_type_of { using type = typename scan_op_value<F>::type; };
 template <class F> struct scan_value_type_of<F, std::void_t<typename F::value_type>> { using type = typename F::value_type; };
 }  // namespace Impl
 

@@ -1,14 +1,14 @@
 // kb200/View.hpp -- View<T*>-style device allocations for the B200 execution space.
 //
 // Covers what the hot path needs of core/src/Kokkos_View.hpp + core/src/Cuda/Kokkos_CudaSpace.{hpp,cpp}:
-//   * View<T>, View<T*>, View<T**>, View<T***>  (rank 0..3, run-time extents), LayoutLeft / LayoutRight,
+//   * View<T>, View<T*> ... View<T******>  (rank 0..6, run-time extents), LayoutLeft / LayoutRight,
 //     memory spaces B200Space (device, CudaSpace::allocate -> b200_malloc) and HostSpace,
 //     MemoryTraits<Unmanaged> / pointer-wrapping constructors, labels, ref-counted ownership
 //     (impl/Kokkos_SharedAlloc.*), zero-initialisation at allocation (View/Kokkos_ViewAlloc.hpp:100-166 ->
 //     ZeroMemset<B200> = b200_memset_async + fence), WithoutInitializing;
 //   * deep_copy between spaces / from a scalar, create_mirror_view[_and_copy], subview of rank-1 ranges.
 // Device Views default to LayoutLeft as in the reference's Cuda backend (first index fastest).
-// Everything rank>3, strided layouts, static extents and DualView/DynRankView are out of scope
+// Everything rank>6, strided layouts, static extents and DualView/DynRankView are out of scope
 // (SURVEY.md section 2 rows 11, 24).
 #ifndef KB200_VIEW_HPP
 #define KB200_VIEW_HPP
@@ -53,6 +53,10 @@ inline ViewAllocProp view_alloc(const std::string& l, WithoutInitializing_t) { r
 inline ViewAllocProp view_alloc(const std::string& l) { return ViewAllocProp{l, true, nullptr}; }
 inline ViewAllocProp view_alloc(const B200& s, const std::string& l) { return ViewAllocProp{l, true, &s}; }
 inline ViewAllocProp view_alloc(const B200& s, WithoutInitializing_t, const std::string& l) { return ViewAllocProp{l, false, &s}; }
+
+// element proxy of View<..., MemoryTraits<Atomic>> (defined in Atomic.hpp): every read-modify-write through it is atomic
+template <class T>
+struct AtomicDataElement;
 
 namespace Impl {
 template <class D> struct data_type_rank { static constexpr int value = 0; using type = D; };
@@ -104,7 +108,7 @@ class View {
 
  public:
   static constexpr int rank = Impl::data_type_rank<DataType>::value;
-  static_assert(rank <= 3, "kb200::View supports rank 0..3");
+  static_assert(rank <= 6, "kb200::View supports rank 0..6");
   using value_type = typename Impl::data_type_rank<DataType>::type;
   using non_const_value_type = std::remove_const_t<value_type>;
   using memory_space = std::conditional_t<std::is_void<typename props::space>::value, B200Space, typename props::space>;
@@ -114,31 +118,32 @@ class View {
   using execution_space = B200;
   using size_type = size_t;
   using pointer_type = value_type*;
-  using reference_type = value_type&;
+  static constexpr bool is_atomic = (props::traits & Atomic) != 0;  // impl/Kokkos_Atomic_View.hpp: operator() yields an atomic proxy
+  using reference_type = std::conditional_t<is_atomic, AtomicDataElement<value_type>, value_type&>;
   static constexpr bool is_managed = !(props::traits & Unmanaged);
   static constexpr bool is_device = !std::is_same<memory_space, HostSpace>::value;
   using HostMirror = View<std::remove_const_t<DataType>, array_layout, HostSpace>;
   using non_const_type = View<DataType, Props...>;
 
-  KB200_INLINE_FUNCTION View() : m_data(nullptr), m_rec(nullptr) { m_ext[0] = m_ext[1] = m_ext[2] = 0; }
+  KB200_INLINE_FUNCTION View() : m_data(nullptr), m_rec(nullptr) { for (int r = 0; r < 6; ++r) m_ext[r] = 0; }
 
   // allocating constructors
-  explicit View(const std::string& label, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0) { allocate(ViewAllocProp{label, true, nullptr}, n0, n1, n2); }
-  explicit View(const char* label, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0) { allocate(ViewAllocProp{label, true, nullptr}, n0, n1, n2); }
-  explicit View(const ViewAllocProp& p, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0) { allocate(p, n0, n1, n2); }
+  explicit View(const std::string& label, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) { allocate(ViewAllocProp{label, true, nullptr}, n0, n1, n2, n3, n4, n5); }
+  explicit View(const char* label, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) { allocate(ViewAllocProp{label, true, nullptr}, n0, n1, n2, n3, n4, n5); }
+  explicit View(const ViewAllocProp& p, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) { allocate(p, n0, n1, n2, n3, n4, n5); }
   // wrapping (unmanaged) constructor
-  KB200_INLINE_FUNCTION View(pointer_type ptr, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0) : m_data(ptr), m_rec(nullptr) {
-    set_extents(n0, n1, n2);
+  KB200_INLINE_FUNCTION View(pointer_type ptr, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) : m_data(ptr), m_rec(nullptr) {
+    set_extents(n0, n1, n2, n3, n4, n5);
   }
 
   // View over team/thread scratch memory: View<T*, ScratchSpace, Unmanaged>(team.team_scratch(level), n)
   template <class S, class = typename S::is_scratch_tag>
-  KB200_INLINE_FUNCTION View(const S& scratch, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0) : m_rec(nullptr) {
-    set_extents(n0, n1, n2);
+  KB200_INLINE_FUNCTION View(const S& scratch, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) : m_rec(nullptr) {
+    set_extents(n0, n1, n2, n3, n4, n5);
     m_data = static_cast<pointer_type>(scratch.get_shmem_aligned(size() * sizeof(value_type), alignof(value_type) > 8 ? alignof(value_type) : 8));
   }
-  static constexpr size_t shmem_size(size_t n0 = 0, size_t n1 = 0, size_t n2 = 0) {
-    return (rank > 0 ? n0 : 1) * (rank > 1 ? n1 : 1) * (rank > 2 ? n2 : 1) * sizeof(value_type) + 8;
+  static constexpr size_t shmem_size(size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) {
+    return (rank > 0 ? n0 : 1) * (rank > 1 ? n1 : 1) * (rank > 2 ? n2 : 1) * (rank > 3 ? n3 : 1) * (rank > 4 ? n4 : 1) * (rank > 5 ? n5 : 1) * sizeof(value_type) + 8;
   }
 
   KB200_INLINE_FUNCTION View(const View& o) : m_data(o.m_data), m_rec(o.m_rec) { copy_ext(o); retain(); }
@@ -147,7 +152,7 @@ class View {
   template <class D2, class... P2, class = std::enable_if_t<std::is_convertible<typename View<D2, P2...>::pointer_type, pointer_type>::value &&
                                                             View<D2, P2...>::rank == rank>>
   KB200_INLINE_FUNCTION View(const View<D2, P2...>& o) : m_data(o.data()), m_rec(is_managed ? o.impl_record() : nullptr) {
-    m_ext[0] = o.extent(0); m_ext[1] = o.extent(1); m_ext[2] = o.extent(2);
+    for (int r = 0; r < 6; ++r) m_ext[r] = o.extent(r);
     retain();
   }
   KB200_INLINE_FUNCTION View& operator=(const View& o) {
@@ -162,20 +167,35 @@ class View {
 
   // element access
   template <int R = rank, std::enable_if_t<R == 0, int> = 0>
-  KB200_FORCEINLINE_FUNCTION reference_type operator()() const { return *m_data; }
+  KB200_FORCEINLINE_FUNCTION reference_type operator()() const { return ref(0); }
   template <class I0, int R = rank, std::enable_if_t<R == 1, int> = 0>
-  KB200_FORCEINLINE_FUNCTION reference_type operator()(const I0 i0) const { return m_data[i0]; }
+  KB200_FORCEINLINE_FUNCTION reference_type operator()(const I0 i0) const { return ref((size_t)i0); }
   template <class I0, int R = rank, std::enable_if_t<R == 1, int> = 0>
-  KB200_FORCEINLINE_FUNCTION reference_type operator[](const I0 i0) const { return m_data[i0]; }
+  KB200_FORCEINLINE_FUNCTION reference_type operator[](const I0 i0) const { return ref((size_t)i0); }
   template <class I0, class I1, int R = rank, std::enable_if_t<R == 2, int> = 0>
   KB200_FORCEINLINE_FUNCTION reference_type operator()(const I0 i0, const I1 i1) const {
-    if constexpr (std::is_same<array_layout, LayoutLeft>::value) return m_data[(size_t)i0 + m_ext[0] * (size_t)i1];
-    else return m_data[(size_t)i1 + m_ext[1] * (size_t)i0];
+    if constexpr (std::is_same<array_layout, LayoutLeft>::value) return ref((size_t)i0 + m_ext[0] * (size_t)i1);
+    else return ref((size_t)i1 + m_ext[1] * (size_t)i0);
   }
   template <class I0, class I1, class I2, int R = rank, std::enable_if_t<R == 3, int> = 0>
   KB200_FORCEINLINE_FUNCTION reference_type operator()(const I0 i0, const I1 i1, const I2 i2) const {
-    if constexpr (std::is_same<array_layout, LayoutLeft>::value) return m_data[(size_t)i0 + m_ext[0] * ((size_t)i1 + m_ext[1] * (size_t)i2)];
-    else return m_data[(size_t)i2 + m_ext[2] * ((size_t)i1 + m_ext[1] * (size_t)i0)];
+    if constexpr (std::is_same<array_layout, LayoutLeft>::value) return ref((size_t)i0 + m_ext[0] * ((size_t)i1 + m_ext[1] * (size_t)i2));
+    else return ref((size_t)i2 + m_ext[2] * ((size_t)i1 + m_ext[1] * (size_t)i0));
+  }
+
+  // rank 4..6: generic mixed-radix offset (LayoutLeft: first index fastest; LayoutRight: last index fastest)
+  template <class... Is, int R = rank, std::enable_if_t<(R >= 4) && sizeof...(Is) == (size_t)R, int> = 0>
+  KB200_FORCEINLINE_FUNCTION reference_type operator()(const Is... is) const {
+    const size_t ix[sizeof...(Is)] = {(size_t)is...};
+    size_t off = 0;
+    if constexpr (std::is_same<array_layout, LayoutLeft>::value) {
+#pragma unroll
+      for (int r = rank - 1; r >= 0; --r) off = off * m_ext[r] + ix[r];
+    } else {
+#pragma unroll
+      for (int r = 0; r < rank; ++r) off = off * m_ext[r] + ix[r];
+    }
+    return ref(off);
   }
 
   KB200_FORCEINLINE_FUNCTION pointer_type data() const { return m_data; }
@@ -199,10 +219,15 @@ class View {
   void impl_window(size_t offset, size_t count) { m_data += offset; m_ext[0] = count; }
 
  private:
-  KB200_INLINE_FUNCTION void set_extents(size_t n0, size_t n1, size_t n2) {
-    m_ext[0] = rank > 0 ? n0 : 1; m_ext[1] = rank > 1 ? n1 : 1; m_ext[2] = rank > 2 ? n2 : 1;
+  KB200_FORCEINLINE_FUNCTION reference_type ref(size_t off) const {
+    if constexpr (is_atomic) return reference_type(m_data + off);
+    else return m_data[off];
   }
-  KB200_INLINE_FUNCTION void copy_ext(const View& o) { m_ext[0] = o.m_ext[0]; m_ext[1] = o.m_ext[1]; m_ext[2] = o.m_ext[2]; }
+  KB200_INLINE_FUNCTION void set_extents(size_t n0, size_t n1, size_t n2, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) {
+    m_ext[0] = rank > 0 ? n0 : 1; m_ext[1] = rank > 1 ? n1 : 1; m_ext[2] = rank > 2 ? n2 : 1;
+    m_ext[3] = rank > 3 ? n3 : 1; m_ext[4] = rank > 4 ? n4 : 1; m_ext[5] = rank > 5 ? n5 : 1;
+  }
+  KB200_INLINE_FUNCTION void copy_ext(const View& o) { for (int r = 0; r < 6; ++r) m_ext[r] = o.m_ext[r]; }
   KB200_INLINE_FUNCTION void retain() {
 #ifndef __CUDA_ARCH__
     if (m_rec) __atomic_add_fetch(&m_rec->refcount, 1, __ATOMIC_RELAXED);
@@ -213,9 +238,9 @@ class View {
     if (m_rec) { Impl::release(m_rec); m_rec = nullptr; }
 #endif
   }
-  void allocate(const ViewAllocProp& p, size_t n0, size_t n1, size_t n2) {
+  void allocate(const ViewAllocProp& p, size_t n0, size_t n1, size_t n2, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) {
     static_assert(!std::is_const<value_type>::value, "cannot allocate a View of const");
-    set_extents(n0, n1, n2);
+    set_extents(n0, n1, n2, n3, n4, n5);
     const size_t bytes = size() * sizeof(value_type);
     m_rec = new Impl::AllocRecord();
     m_rec->label = p.label;
@@ -248,7 +273,7 @@ class View {
   }
 
   pointer_type m_data;
-  size_t m_ext[3];
+  size_t m_ext[6];
   Impl::AllocRecord* m_rec;
 };
 
@@ -302,16 +327,39 @@ void deep_copy(const View<D1, P1...>& dst, const View<D2, P2...>& src) {
   space.fence("kb200::deep_copy: fence after copy");
 }
 
+// deep_copy(scalar, rank-0 View) / deep_copy(rank-0 View, scalar)  (core/src/Kokkos_CopyViews.hpp:1116-1160)
+template <class T, class D, class... P, class = std::enable_if_t<View<D, P...>::rank == 0 && std::is_same<T, typename View<D, P...>::non_const_value_type>::value>>
+void deep_copy(T& dst, const View<D, P...>& src) {
+  B200 space;
+  Impl::copy_bytes<HostSpace, typename View<D, P...>::memory_space>(space, &dst, src.data(), sizeof(T));
+  space.fence("kb200::deep_copy(scalar, View)");
+}
+namespace Impl {
+// Kokkos::Impl::DeepCopy<DstSpace, SrcSpace>(dst, src, bytes): raw byte copy between memory spaces, used as a constructor call
+// (core/src/Cuda/Kokkos_CudaSpace.hpp:473-590); blocking like the reference's no-exec-space form
+template <class DstSpace, class SrcSpace, class Exec = B200>
+struct DeepCopy {
+  DeepCopy(void* dst, const void* src, size_t bytes) {
+    B200 space;
+    copy_bytes<typename DstSpace::memory_space, typename SrcSpace::memory_space>(space, dst, src, bytes);
+    space.fence("kb200::Impl::DeepCopy");
+  }
+  DeepCopy(const B200& space, void* dst, const void* src, size_t bytes) {
+    copy_bytes<typename DstSpace::memory_space, typename SrcSpace::memory_space>(space, dst, src, bytes);
+  }
+};
+}  // namespace Impl
+
 template <class D, class... P>
 typename View<D, P...>::HostMirror create_mirror_view(const View<D, P...>& v) {
-  return typename View<D, P...>::HostMirror(view_alloc(WithoutInitializing, v.label() + "_mirror"), v.extent(0), v.extent(1), v.extent(2));
+  return typename View<D, P...>::HostMirror(view_alloc(WithoutInitializing, v.label() + "_mirror"), v.extent(0), v.extent(1), v.extent(2), v.extent(3), v.extent(4), v.extent(5));
 }
 template <class D, class... P>
 typename View<D, P...>::HostMirror create_mirror(const View<D, P...>& v) { return create_mirror_view(v); }
 template <class Space, class D, class... P>
 auto create_mirror_view_and_copy(const Space&, const View<D, P...>& v) {
   using Dst = View<std::remove_const_t<D>, typename View<D, P...>::array_layout, typename Space::memory_space>;
-  Dst d(view_alloc(WithoutInitializing, v.label() + "_copy"), v.extent(0), v.extent(1), v.extent(2));
+  Dst d(view_alloc(WithoutInitializing, v.label() + "_copy"), v.extent(0), v.extent(1), v.extent(2), v.extent(3), v.extent(4), v.extent(5));
   deep_copy(d, v);
   return d;
 }

@@ -27,7 +27,9 @@ constexpr unsigned kFullMask = 0xffffffffu;
 // ---- shuffles of arbitrary trivially-copyable values, as N 32-bit words ------------------
 template <class T, class ShflOp>
 KB200_DEVICE_FUNCTION T shfl_words(const T& v, ShflOp op) {
-  static_assert(std::is_trivially_copyable<T>::value, "reduction value_type must be trivially copyable");
+  // Kokkos moves reduction values between threads bit-wise; user types with hand-written (but member-wise) copy operations
+  // are accepted like the reference does (e.g. MyComplex in incremental/Test14_MDRangeReduce.hpp:30-52)
+  static_assert(std::is_trivially_destructible<T>::value, "reduction value_type must be bit-wise movable (trivially destructible)");
   constexpr int W = (sizeof(T) + 3) / 4;
   unsigned w[W];
 #pragma unroll
