@@ -6,6 +6,9 @@
 #define KB200_COMPAT_HPP
 
 #include "View.hpp"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <typeinfo>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -45,8 +48,9 @@ inline void kokkos_free(void* p) { Impl::raw_deallocate<typename Space::memory_s
 
 KB200_INLINE_FUNCTION void abort(const char* msg) {
 #ifdef __CUDA_ARCH__
-  printf("kb200::abort: %s\n", msg);
-  __trap();
+  // device-side assertion: the message reaches the host's stderr and the context fails with cudaErrorAssert
+  // (core/src/Cuda/Kokkos_Abort.hpp does the same)
+  __assert_fail(msg, "kb200::abort", 0, "");
 #else
   std::fprintf(stderr, "kb200::abort: %s\n", msg);
   std::abort();
@@ -56,6 +60,80 @@ KB200_INLINE_FUNCTION void abort(const char* msg) {
 struct ParallelForTag {};     // core/src/Kokkos_Core_fwd.hpp: pattern tags for team_size_max / team_size_recommended
 struct ParallelReduceTag {};
 struct ParallelScanTag {};
+
+// Kokkos::printf (core/src/Kokkos_Printf.hpp): callable from host and device code
+template <class... Args>
+KB200_FORCEINLINE_FUNCTION void printf(const char* fmt, Args... args) {
+  if constexpr (sizeof...(Args) == 0) ::printf("%s", fmt);
+  else ::printf(fmt, args...);
+}
+
+// Kokkos::pair (core/src/Kokkos_Pair.hpp): std::pair usable in device code
+template <class T1, class T2>
+struct pair {
+  using first_type = T1;
+  using second_type = T2;
+  T1 first;
+  T2 second;
+  KB200_DEFAULTED_FUNCTION constexpr pair() = default;
+  KB200_FORCEINLINE_FUNCTION constexpr pair(const T1& f, const T2& s) : first(f), second(s) {}
+  template <class U, class V>
+  KB200_FORCEINLINE_FUNCTION constexpr pair(const pair<U, V>& p) : first(p.first), second(p.second) {}
+  template <class U, class V>
+  pair(const std::pair<U, V>& p) : first(p.first), second(p.second) {}
+  std::pair<T1, T2> to_std_pair() const { return std::make_pair(first, second); }
+};
+template <class T1, class T2>
+KB200_FORCEINLINE_FUNCTION constexpr bool operator==(const pair<T1, T2>& a, const pair<T1, T2>& b) { return a.first == b.first && a.second == b.second; }
+template <class T1, class T2>
+KB200_FORCEINLINE_FUNCTION constexpr bool operator!=(const pair<T1, T2>& a, const pair<T1, T2>& b) { return !(a == b); }
+template <class T1, class T2>
+KB200_FORCEINLINE_FUNCTION constexpr bool operator<(const pair<T1, T2>& a, const pair<T1, T2>& b) {
+  return a.first < b.first || (!(b.first < a.first) && a.second < b.second);
+}
+template <class T1, class T2>
+KB200_FORCEINLINE_FUNCTION constexpr pair<T1, T2> make_pair(T1 a, T2 b) { return pair<T1, T2>(a, b); }
+
+// Kokkos math functions used in functors (core/src/Kokkos_MathematicalFunctions.hpp, Kokkos_MinMax.hpp).  Only declared in
+// Kokkos-namespace mode: a translation unit that says `using namespace kb200;` before CUDA's math headers would otherwise see
+// two candidates for every unqualified sqrt()/fabs() call inside those headers.
+#ifdef KB200_AS_KOKKOS
+template <class T> KB200_FORCEINLINE_FUNCTION constexpr const T& min(const T& a, const T& b) { return b < a ? b : a; }
+template <class T> KB200_FORCEINLINE_FUNCTION constexpr const T& max(const T& a, const T& b) { return a < b ? b : a; }
+template <class T> KB200_FORCEINLINE_FUNCTION constexpr const T& clamp(const T& v, const T& lo, const T& hi) { return v < lo ? lo : (hi < v ? hi : v); }
+#define KB200_MATH_1(NAME) \
+  KB200_FORCEINLINE_FUNCTION double NAME(double x) { return ::NAME(x); } \
+  KB200_FORCEINLINE_FUNCTION float NAME(float x) { return ::NAME##f(x); }
+KB200_MATH_1(sqrt) KB200_MATH_1(fabs) KB200_MATH_1(exp) KB200_MATH_1(log) KB200_MATH_1(sin) KB200_MATH_1(cos) KB200_MATH_1(floor) KB200_MATH_1(ceil)
+#undef KB200_MATH_1
+KB200_FORCEINLINE_FUNCTION double fmin(double a, double b) { return ::fmin(a, b); }
+KB200_FORCEINLINE_FUNCTION double fmax(double a, double b) { return ::fmax(a, b); }
+KB200_FORCEINLINE_FUNCTION float fmin(float a, float b) { return ::fminf(a, b); }
+KB200_FORCEINLINE_FUNCTION float fmax(float a, float b) { return ::fmaxf(a, b); }
+KB200_FORCEINLINE_FUNCTION double pow(double a, double b) { return ::pow(a, b); }
+template <class T, class = std::enable_if_t<std::is_arithmetic<T>::value>>
+KB200_FORCEINLINE_FUNCTION T abs(T x) { return x < T(0) ? T(-x) : x; }
+#endif  // KB200_AS_KOKKOS
+
+namespace Experimental {
+using half_t = __half;          // core/src/Kokkos_Half_FloatingPointWrapper.hpp (sm_100 has native fp16 / bf16)
+using bhalf_t = __nv_bfloat16;
+// Kokkos::Experimental::require(policy, WorkItemProperty): launch hints; accepted and ignored on this backend
+namespace WorkItemProperty {
+struct HintLightWeight_t {};
+struct HintHeavyWeight_t {};
+struct None_t {};
+constexpr HintLightWeight_t HintLightWeight{};
+constexpr HintHeavyWeight_t HintHeavyWeight{};
+constexpr None_t None{};
+}  // namespace WorkItemProperty
+template <class Policy, class Property>
+inline Policy require(const Policy& p, Property) { return p; }
+}  // namespace Experimental
+namespace Impl {
+template <class T>
+struct TypeInfo { static std::string name() { return typeid(T).name(); } };  // core/src/impl/Kokkos_TypeInfo.hpp
+}  // namespace Impl
 
 class Timer {  // core/src/Kokkos_Timer.hpp
   std::chrono::steady_clock::time_point m_t0 = std::chrono::steady_clock::now();

@@ -12,6 +12,7 @@
 #define KB200_INLINE_FUNCTION __host__ __device__ inline
 #define KB200_FORCEINLINE_FUNCTION __host__ __device__ __forceinline__
 #define KB200_DEVICE_FUNCTION __device__ __forceinline__
+#define KB200_DEFAULTED_FUNCTION __host__ __device__ inline
 #define KB200_LAMBDA [=] __host__ __device__
 #define KB200_CLASS_LAMBDA [ =, *this ] __host__ __device__
 

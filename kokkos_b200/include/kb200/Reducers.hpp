@@ -90,8 +90,15 @@ struct ReducerBase {
   value_type* m_ptr;
   bool m_scalar;
   KB200_INLINE_FUNCTION ReducerBase(value_type& v) : m_ptr(&v), m_scalar(true) {}
+  // result View: device memory => written by the kernel (asynchronous); host-space View => treated like a scalar (the value
+  // is stored after the wait, core/src/Cuda/Kokkos_Cuda_Parallel_Range.hpp:344-360 "result ptr host accessible")
+  template <class ViewLike, class = void>
+  struct view_on_host : std::false_type {};
+  template <class ViewLike>
+  struct view_on_host<ViewLike, std::void_t<typename ViewLike::memory_space>>
+      : std::integral_constant<bool, !ViewLike::is_device> {};
   template <class ViewLike, class = decltype(std::declval<const ViewLike&>().data())>
-  KB200_INLINE_FUNCTION ReducerBase(const ViewLike& v, int = 0) : m_ptr(v.data()), m_scalar(false) {}
+  KB200_INLINE_FUNCTION ReducerBase(const ViewLike& v, int = 0) : m_ptr(v.data()), m_scalar(view_on_host<ViewLike>::value) {}
   KB200_INLINE_FUNCTION value_type& reference() const { return *m_ptr; }
   KB200_INLINE_FUNCTION value_type* data() const { return m_ptr; }
   KB200_INLINE_FUNCTION bool references_scalar() const { return m_scalar; }
