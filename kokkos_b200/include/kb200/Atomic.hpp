@@ -360,6 +360,46 @@ KB200_FORCEINLINE_FUNCTION void atomic_store(T* p, std::common_type_t<T> v) {
   KB200_ATOMIC_DISPATCH(Impl::dev::atomic_store(p, v);, __atomic_store(p, &v, __ATOMIC_RELAXED);)
 }
 
+// op_fetch forms (return the NEW value) and the remaining fetch_op forms of the desul wrapper
+// (core/src/Kokkos_Atomics_Desul_Wrapper.hpp:72-148): mod / shifts / nand go through the CAS loop.
+template <class T> KB200_FORCEINLINE_FUNCTION T atomic_fetch_mod(T* p, std::common_type_t<T> v) {
+  KB200_ATOMIC_DISPATCH(return Impl::cas_loop(p, [=](T o) { return (T)(o % v); });, return Impl::host_rmw(p, [=](T o) { return (T)(o % v); });)
+}
+template <class T> KB200_FORCEINLINE_FUNCTION T atomic_fetch_nand(T* p, std::common_type_t<T> v) {
+  KB200_ATOMIC_DISPATCH(return Impl::cas_loop(p, [=](T o) { return (T)(~(o & v)); });, return Impl::host_rmw(p, [=](T o) { return (T)(~(o & v)); });)
+}
+template <class T> KB200_FORCEINLINE_FUNCTION T atomic_fetch_lshift(T* p, unsigned v) {
+  KB200_ATOMIC_DISPATCH(return Impl::cas_loop(p, [=](T o) { return (T)(o << v); });, return Impl::host_rmw(p, [=](T o) { return (T)(o << v); });)
+}
+template <class T> KB200_FORCEINLINE_FUNCTION T atomic_fetch_rshift(T* p, unsigned v) {
+  KB200_ATOMIC_DISPATCH(return Impl::cas_loop(p, [=](T o) { return (T)(o >> v); });, return Impl::host_rmw(p, [=](T o) { return (T)(o >> v); });)
+}
+template <class T> KB200_FORCEINLINE_FUNCTION void atomic_mod(T* p, std::common_type_t<T> v) { (void)atomic_fetch_mod(p, v); }
+template <class T> KB200_FORCEINLINE_FUNCTION void atomic_nand(T* p, std::common_type_t<T> v) { (void)atomic_fetch_nand(p, v); }
+template <class T> KB200_FORCEINLINE_FUNCTION void atomic_lshift(T* p, unsigned v) { (void)atomic_fetch_lshift(p, v); }
+template <class T> KB200_FORCEINLINE_FUNCTION void atomic_rshift(T* p, unsigned v) { (void)atomic_fetch_rshift(p, v); }
+#define KB200_ATOMIC_OP_FETCH(NAME, FETCH, EXPR)                                                          \
+  template <class T>                                                                                      \
+  KB200_FORCEINLINE_FUNCTION T NAME(T* p, std::common_type_t<T> v) {                                       \
+    const T o = FETCH(p, v);                                                                              \
+    return (T)(EXPR);                                                                                     \
+  }
+KB200_ATOMIC_OP_FETCH(atomic_add_fetch, atomic_fetch_add, o + v)
+KB200_ATOMIC_OP_FETCH(atomic_sub_fetch, atomic_fetch_sub, o - v)
+KB200_ATOMIC_OP_FETCH(atomic_max_fetch, atomic_fetch_max, v > o ? v : o)
+KB200_ATOMIC_OP_FETCH(atomic_min_fetch, atomic_fetch_min, v < o ? v : o)
+KB200_ATOMIC_OP_FETCH(atomic_mul_fetch, atomic_fetch_mul, o * v)
+KB200_ATOMIC_OP_FETCH(atomic_div_fetch, atomic_fetch_div, o / v)
+KB200_ATOMIC_OP_FETCH(atomic_mod_fetch, atomic_fetch_mod, o % v)
+KB200_ATOMIC_OP_FETCH(atomic_and_fetch, atomic_fetch_and, o & v)
+KB200_ATOMIC_OP_FETCH(atomic_or_fetch, atomic_fetch_or, o | v)
+KB200_ATOMIC_OP_FETCH(atomic_xor_fetch, atomic_fetch_xor, o ^ v)
+KB200_ATOMIC_OP_FETCH(atomic_nand_fetch, atomic_fetch_nand, ~(o & v))
+#undef KB200_ATOMIC_OP_FETCH
+template <class T> KB200_FORCEINLINE_FUNCTION T atomic_lshift_fetch(T* p, unsigned v) { return (T)(atomic_fetch_lshift(p, v) << v); }
+template <class T> KB200_FORCEINLINE_FUNCTION T atomic_rshift_fetch(T* p, unsigned v) { return (T)(atomic_fetch_rshift(p, v) >> v); }
+template <class T> KB200_FORCEINLINE_FUNCTION T atomic_inc_fetch(T* p) { return atomic_add_fetch(p, T(1)); }
+template <class T> KB200_FORCEINLINE_FUNCTION T atomic_dec_fetch(T* p) { return atomic_sub_fetch(p, T(1)); }
 
 // ---- element proxy of atomic Views: View<T*, MemoryTraits<Atomic>>::operator() returns this (core/src/impl/Kokkos_Atomic_View.hpp:
 //      AtomicDataElement); every operator is one atomic operation on the referenced element.

@@ -235,6 +235,142 @@ void parallel_reduce(size_t n, const F& f, R&& result) {
 }
 
 // =====================================================================================================
+// parallel_reduce with several results: parallel_reduce(label, policy, f, r0, r1, ...)   (row a22)
+// =====================================================================================================
+// The reference packs N reducers into one struct value_type and funnels it through the ordinary reduction
+// (core/src/impl/Kokkos_Combined_Reducer.hpp:273-288,389-404,533-581).  Same here: the values travel as one trivially
+// copyable CombinedValue through the register/shuffle/ticket machinery; the functor is called as f(i..., v0, v1, ...).
+// Each result may be a scalar reference or a rank-0 View (summed), or any reducer object.  The call blocks, then each
+// component is written to its destination (the reference fences as well, :567-580).
+namespace Impl {
+template <class... Vs> struct CombinedValue;
+template <> struct CombinedValue<> {};
+template <class V0, class... Vs>
+struct CombinedValue<V0, Vs...> { V0 head; CombinedValue<Vs...> tail; };
+template <int I, class V0, class... Vs>
+KB200_FORCEINLINE_FUNCTION auto& combined_get(CombinedValue<V0, Vs...>& v) {
+  if constexpr (I == 0) return v.head; else return combined_get<I - 1>(v.tail);
+}
+template <int I, class V0, class... Vs>
+KB200_FORCEINLINE_FUNCTION const auto& combined_get(const CombinedValue<V0, Vs...>& v) {
+  if constexpr (I == 0) return v.head; else return combined_get<I - 1>(v.tail);
+}
+
+// how one result argument takes part: value type, reducer, and where the value goes afterwards
+template <class R, class = void>
+struct combined_slot {  // plain scalar reference: summed
+  using value_type = std::remove_reference_t<R>;
+  using reducer_type = DefaultSumReducer<value_type>;
+  static reducer_type reducer(R&) { return {}; }
+  static void store(const B200&, R& dst, const value_type& v) { dst = v; }
+};
+template <class R>
+struct combined_slot<R, std::enable_if_t<is_view_v<R>>> {  // rank-0 View: summed
+  using VT = std::decay_t<R>;
+  using value_type = typename VT::non_const_value_type;
+  using reducer_type = DefaultSumReducer<value_type>;
+  static reducer_type reducer(const VT&) { return {}; }
+  static void store(const B200& space, const VT& dst, const value_type& v) {
+    copy_bytes<typename VT::memory_space, HostSpace>(space, (void*)dst.data(), &v, sizeof(value_type));
+  }
+};
+template <class R>
+struct combined_slot<R, std::enable_if_t<is_reducer_v<std::decay_t<R>>>> {  // reducer object
+  using RD = std::decay_t<R>;
+  using value_type = typename RD::value_type;
+  using reducer_type = ReducerAdapter<RD>;
+  static reducer_type reducer(const RD& r) { return reducer_type{r}; }
+  static void store(const B200& space, const RD& r, const value_type& v) {
+    if (r.references_scalar()) r.reference() = v;
+    else throw_on_error(b200_memcpy_h2d_async(space.impl_instance(), (void*)r.data(), &v, sizeof(value_type)));
+  }
+};
+
+template <class... Rs> struct CombinedReducers;
+template <> struct CombinedReducers<> {
+  template <class CV> KB200_FORCEINLINE_FUNCTION void init(CV&) const {}
+  template <class CV> KB200_FORCEINLINE_FUNCTION void join(CV&, const CV&) const {}
+  template <class CV> KB200_FORCEINLINE_FUNCTION void final(CV&) const {}
+};
+template <class R0, class... Rs>
+struct CombinedReducers<R0, Rs...> {
+  R0 head;
+  CombinedReducers<Rs...> tail;
+  template <class CV> KB200_FORCEINLINE_FUNCTION void init(CV& v) const { head.init(v.head); tail.init(v.tail); }
+  template <class CV> KB200_FORCEINLINE_FUNCTION void join(CV& d, const CV& s) const { head.join(d.head, s.head); tail.join(d.tail, s.tail); }
+  template <class CV> KB200_FORCEINLINE_FUNCTION void final(CV& v) const { head.final(v.head); tail.final(v.tail); }
+};
+template <class CV, class... Rs>
+struct CombinedReducer {
+  using value_type = CV;
+  CombinedReducers<Rs...> rs;
+  KB200_FORCEINLINE_FUNCTION void init(CV& v) const { rs.init(v); }
+  KB200_FORCEINLINE_FUNCTION void join(CV& d, const CV& s) const { rs.join(d, s); }
+  KB200_FORCEINLINE_FUNCTION void final(CV& v) const { rs.final(v); }
+};
+inline CombinedReducers<> make_combined_reducers() { return {}; }
+template <class R0, class... Rs>
+CombinedReducers<R0, Rs...> make_combined_reducers(const R0& r0, const Rs&... rs) { return CombinedReducers<R0, Rs...>{r0, make_combined_reducers(rs...)}; }
+
+// calls f(leading args..., v0, v1, ...): leading args are the index / indices / team handle (and the work tag)
+template <class F, class CV, int N>
+struct CombinedFunctor {
+  F f;
+  template <class... Lead, size_t... Is>
+  KB200_FORCEINLINE_FUNCTION void call(CV& v, std::index_sequence<Is...>, Lead&&... lead) const {
+    f(static_cast<Lead&&>(lead)..., combined_get<(int)Is>(v)...);
+  }
+  template <class A0> KB200_FORCEINLINE_FUNCTION void operator()(A0&& a0, CV& v) const { call(v, std::make_index_sequence<N>{}, static_cast<A0&&>(a0)); }
+  template <class A0, class A1> KB200_FORCEINLINE_FUNCTION void operator()(A0&& a0, A1&& a1, CV& v) const {
+    call(v, std::make_index_sequence<N>{}, static_cast<A0&&>(a0), static_cast<A1&&>(a1)); }
+  template <class A0, class A1, class A2> KB200_FORCEINLINE_FUNCTION void operator()(A0&& a0, A1&& a1, A2&& a2, CV& v) const {
+    call(v, std::make_index_sequence<N>{}, static_cast<A0&&>(a0), static_cast<A1&&>(a1), static_cast<A2&&>(a2)); }
+  template <class A0, class A1, class A2, class A3> KB200_FORCEINLINE_FUNCTION void operator()(A0&& a0, A1&& a1, A2&& a2, A3&& a3, CV& v) const {
+    call(v, std::make_index_sequence<N>{}, static_cast<A0&&>(a0), static_cast<A1&&>(a1), static_cast<A2&&>(a2), static_cast<A3&&>(a3)); }
+  template <class A0, class A1, class A2, class A3, class A4> KB200_FORCEINLINE_FUNCTION void operator()(A0&& a0, A1&& a1, A2&& a2, A3&& a3, A4&& a4, CV& v) const {
+    call(v, std::make_index_sequence<N>{}, static_cast<A0&&>(a0), static_cast<A1&&>(a1), static_cast<A2&&>(a2), static_cast<A3&&>(a3), static_cast<A4&&>(a4)); }
+  template <class A0, class A1, class A2, class A3, class A4, class A5> KB200_FORCEINLINE_FUNCTION void operator()(A0&& a0, A1&& a1, A2&& a2, A3&& a3, A4&& a4, A5&& a5, CV& v) const {
+    call(v, std::make_index_sequence<N>{}, static_cast<A0&&>(a0), static_cast<A1&&>(a1), static_cast<A2&&>(a2), static_cast<A3&&>(a3), static_cast<A4&&>(a4), static_cast<A5&&>(a5)); }
+  template <class A0, class A1, class A2, class A3, class A4, class A5, class A6> KB200_FORCEINLINE_FUNCTION void operator()(A0&& a0, A1&& a1, A2&& a2, A3&& a3, A4&& a4, A5&& a5, A6&& a6, CV& v) const {
+    call(v, std::make_index_sequence<N>{}, static_cast<A0&&>(a0), static_cast<A1&&>(a1), static_cast<A2&&>(a2), static_cast<A3&&>(a3), static_cast<A4&&>(a4), static_cast<A5&&>(a5), static_cast<A6&&>(a6)); }
+};
+
+template <class CV, class... Rs, size_t... Is>
+void combined_store(const B200& space, const CV& v, std::index_sequence<Is...>, Rs&&... rs) {
+  (combined_slot<Rs>::store(space, rs, combined_get<(int)Is>(v)), ...);
+}
+template <class Policy, class F, class... Rs>
+void combined_reduce_entry(const Policy& policy, const F& f, Rs&&... rs) {
+  using CV = CombinedValue<typename combined_slot<Rs>::value_type...>;
+  using Red = CombinedReducer<CV, typename combined_slot<Rs>::reducer_type...>;
+  Red red{make_combined_reducers(combined_slot<Rs>::reducer(rs)...)};
+  CombinedFunctor<F, CV, (int)sizeof...(Rs)> cf{f};
+  CV result;
+  red.init(result);
+  reduce_dispatch(policy, cf, red, ResultTarget<CV>{&result, nullptr});
+  combined_store(policy.space(), result, std::index_sequence_for<Rs...>{}, static_cast<Rs&&>(rs)...);
+  policy.space().fence("kb200::parallel_reduce(combined): results delivered");
+}
+}  // namespace Impl
+
+template <class Policy, class F, class R0, class R1, class... Rs, class = std::enable_if_t<Impl::is_policy<Policy>::value>>
+void parallel_reduce(const std::string& /*label*/, const Policy& policy, const F& f, R0&& r0, R1&& r1, Rs&&... rs) {
+  Impl::combined_reduce_entry(policy, f, static_cast<R0&&>(r0), static_cast<R1&&>(r1), static_cast<Rs&&>(rs)...);
+}
+template <class Policy, class F, class R0, class R1, class... Rs, class = std::enable_if_t<Impl::is_policy<Policy>::value>>
+void parallel_reduce(const Policy& policy, const F& f, R0&& r0, R1&& r1, Rs&&... rs) {
+  Impl::combined_reduce_entry(policy, f, static_cast<R0&&>(r0), static_cast<R1&&>(r1), static_cast<Rs&&>(rs)...);
+}
+template <class F, class R0, class R1, class... Rs>
+void parallel_reduce(const std::string& /*label*/, size_t n, const F& f, R0&& r0, R1&& r1, Rs&&... rs) {
+  Impl::combined_reduce_entry(RangePolicy<>(0, (long long)n), f, static_cast<R0&&>(r0), static_cast<R1&&>(r1), static_cast<Rs&&>(rs)...);
+}
+template <class F, class R0, class R1, class... Rs>
+void parallel_reduce(size_t n, const F& f, R0&& r0, R1&& r1, Rs&&... rs) {
+  Impl::combined_reduce_entry(RangePolicy<>(0, (long long)n), f, static_cast<R0&&>(r0), static_cast<R1&&>(r1), static_cast<Rs&&>(rs)...);
+}
+
+// =====================================================================================================
 // parallel_scan (RangePolicy)
 // =====================================================================================================
 namespace Impl {

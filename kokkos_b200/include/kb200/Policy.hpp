@@ -52,10 +52,12 @@ template <> struct policy_traits<> {
 template <class F, class... R>
 struct policy_traits<F, R...> {
   using next = policy_traits<R...>;
-  static constexpr bool known = is_schedule<F>::value || is_index_type<F>::value || is_launch_bounds<F>::value ||
+  // a bare integral type is an index type too (RangePolicy<Space, long>: impl/Kokkos_AnalyzePolicy.hpp:165-190)
+  static constexpr bool is_index = is_index_type<F>::value || std::is_integral<F>::value;
+  static constexpr bool known = is_schedule<F>::value || is_index || is_launch_bounds<F>::value ||
                                 is_rank<F>::value || is_exec_space<F>::value;
   using schedule = std::conditional_t<is_schedule<F>::value, F, typename next::schedule>;
-  using index = std::conditional_t<is_index_type<F>::value, F, typename next::index>;
+  using index = std::conditional_t<is_index, std::conditional_t<std::is_integral<F>::value, IndexType<F>, F>, typename next::index>;
   using bounds = std::conditional_t<is_launch_bounds<F>::value, F, typename next::bounds>;
   using rank = std::conditional_t<is_rank<F>::value, F, typename next::rank>;
   using tag = std::conditional_t<!known, F, typename next::tag>;  // anything unrecognised is the work tag
@@ -133,7 +135,9 @@ class MDRangePolicy {
   template <class L, class U, class Tl>
   MDRangePolicy(const B200& s, std::initializer_list<L> lower, std::initializer_list<U> upper, std::initializer_list<Tl> tile) : m_space(s) { init(lower, upper, tile); }
   MDRangePolicy(const point_type& lower, const point_type& upper, const tile_type& tile = tile_type{}) { init_arrays(lower, upper, tile); }
-  MDRangePolicy(const B200& s, const point_type& lower, const point_type& upper, const tile_type& tile = tile_type{}) : m_space(s) { init_arrays(lower, upper, tile); }
+  // (template on the space type: a braced list such as {{0, 0, 0}} must never be considered for the execution-space parameter)
+  template <class S, class = std::enable_if_t<std::is_same<std::decay_t<S>, B200>::value>>
+  MDRangePolicy(const S& s, const point_type& lower, const point_type& upper, const tile_type& tile = tile_type{}) : m_space(s) { init_arrays(lower, upper, tile); }
 
   const B200& space() const { return m_space; }
   point_type m_lower{}, m_upper{};

@@ -183,6 +183,35 @@ int kb200_case_reduce_i32(int op, const int32_t* hx, i64 n, int32_t* out) {
   });
 }
 
+// multi-result parallel_reduce (CombinedReducer, core/unit_test/TestReduce.hpp:545-640 "int_combined_reduce"):
+// out[0..2] = sum, min, max over a RangePolicy; out[3..4] = sum + count over a 3-D MDRangePolicy; out[5] = device-View sum,
+// out[6] = host scalar summed in the same call
+int kb200_case_combined_reduce(const i64* hx, i64 n, i64 n0, i64 n1, i64 n2, i64* out) {
+  return guarded([&] {
+    View<const i64*> x = to_device(hx, n);
+    i64 s = -1, mn = 0, mx = 0;
+    parallel_reduce("combined", RangePolicy<>(0, n), KB200_LAMBDA(const i64 i, i64& a, i64& lo, i64& hi) {
+      a += x(i);
+      if (x(i) < lo) lo = x(i);
+      if (x(i) > hi) hi = x(i);
+    }, s, Min<i64>(mn), Max<i64>(mx));
+    out[0] = s; out[1] = mn; out[2] = mx;
+    i64 s3 = -1, cnt = -1;
+    parallel_reduce("combined_md", MDRangePolicy<Rank<3>>({0, 0, 0}, {n0, n1, n2}), KB200_LAMBDA(const i64 i, const i64 j, const i64 k, i64& a, i64& c) {
+      a += i + 10 * j + 100 * k;
+      c += 1;
+    }, s3, cnt);
+    out[3] = s3; out[4] = cnt;
+    View<i64> dv("dv");
+    i64 hs = -1;
+    parallel_reduce(n, KB200_LAMBDA(const i64 i, i64& a, i64& b) { a += 2 * x(i); b += 1; }, dv, hs);
+    View<i64, HostSpace> hv("hv");
+    deep_copy(hv, dv);
+    out[5] = hv(); out[6] = hs;
+    return 0;
+  });
+}
+
 // ------------------------------------------------------------------ parallel_scan
 int kb200_case_scan_i64(const i64* hx, i64* hy, i64 n, int inclusive, i64* total) {
   return guarded([&] {

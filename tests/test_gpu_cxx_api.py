@@ -94,6 +94,19 @@ def test_range_reduce_int32_redux_and_bitwise(cases, port, n):
     assert out[0] == int(np.any(x == 3))
 
 
+@pytest.mark.parametrize("n", (1, 1000, 100003))
+def test_combined_multi_result_reduce(cases, n):
+    """parallel_reduce(policy, f, r0, r1, ...) -- the CombinedReducer path (row a22): scalars, reducers and a device View."""
+    x = W.c3_wrap(n) >> 20
+    out = np.zeros(8, dtype=np.int64)
+    n0, n1, n2 = 13, 7, 5
+    ok(cases, cases.kb200_case_combined_reduce(P(x), c_int64(n), c_int64(n0), c_int64(n1), c_int64(n2), P(out)))
+    assert (out[0], out[1], out[2]) == (int(x.sum()), int(x.min()), int(x.max()))
+    i, j, k = np.meshgrid(np.arange(n0), np.arange(n1), np.arange(n2), indexing="ij")
+    assert out[3] == int((i + 10 * j + 100 * k).sum()) and out[4] == n0 * n1 * n2
+    assert out[5] == 2 * int(x.sum()) and out[6] == n
+
+
 @pytest.mark.parametrize("n", (0, 1, 2303, 2304, 2305, 100003, 1 << 21))
 def test_generic_scan_lambda(cases, port, n):
     x = W.c3_wrap(n)
