@@ -126,11 +126,15 @@ def run_reference(args, rank):
         pass  # warm-up is inside the reference driver (1 untimed call per measurement)
     t0 = time.perf_counter()
     cb, step_s = cpu_reference_leg(log2n, max(args.steps, 1))
-    line = {"impl": "reference", "metric": "parallel_reduce+parallel_scan HBM-equivalent throughput", "value": cb["value"], "unit": "GB/s",
+    line = {"impl": "reference", "metric": "parallel_reduce+parallel_scan HBM throughput", "value": cb["value"], "unit": "GB/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int64", "data": "synthetic",
-            "config": {"workload": f"reduce Sum<double> + exclusive scan int64, bounded sample 2^{log2n} elements each (the GPU arm runs 2^30 per GPU)",
-                       "policy": "RangePolicy<Kokkos::OpenMP>", "timing": "Kokkos::Timer best of steps after 1 warm-up"},
+            "config": {"workload": f"per GPU: parallel_reduce Sum<double> over View<double*> 2^{LOG2N_DEFAULT} + parallel_scan exclusive over "
+                                   f"View<int64_t*> 2^{LOG2N_DEFAULT} (BASELINE.json configs[0] functor at the target size + configs[2])",
+                       "sample": f"each step = the same two calls on 2^{log2n} elements per View on the host (bounded sample of the workload); "
+                                 "throughput = algorithmic bytes / time, directly comparable",
+                       "policy": "RangePolicy<Kokkos::OpenMP>", "elements_per_view_in_sample": n, "algorithmic_bytes_per_step": 24 * n,
+                       "timing": "Kokkos::Timer around each call, best of `steps` after 1 warm-up; all host threads"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
