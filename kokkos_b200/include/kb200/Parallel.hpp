@@ -27,6 +27,7 @@
 #include "impl/ReduceKernel.hpp"
 #include "impl/ScanGeneric.hpp"
 #include "impl/MDRangeKernel.hpp"
+#include "impl/ArrayReduceKernel.hpp"
 
 namespace kb200 {
 namespace Impl {
@@ -49,6 +50,20 @@ template <class Tag, class F, class V, class = void> struct has_tagged_join : st
 template <class Tag, class F, class V>
 struct has_tagged_join<Tag, F, V, std::void_t<decltype(std::declval<const F&>().join(std::declval<Tag>(), std::declval<V&>(), std::declval<const V&>()))>> : std::true_type {};
 
+template <class Tag, class F, class V, class = void> struct has_tagged_init : std::false_type {};
+template <class Tag, class F, class V>
+struct has_tagged_init<Tag, F, V, std::void_t<decltype(std::declval<const F&>().init(std::declval<Tag>(), std::declval<V&>()))>> : std::true_type {};
+template <class Tag, class F, class V, class = void> struct has_tagged_final : std::false_type {};
+template <class Tag, class F, class V>
+struct has_tagged_final<Tag, F, V, std::void_t<decltype(std::declval<const F&>().final(std::declval<Tag>(), std::declval<V&>()))>> : std::true_type {};
+// does the functor bring any of init / join / final (plain or tagged with the policy's work tag)?
+template <class F, class V, class Tag, bool = std::is_void<Tag>::value>
+struct brings_reduction_members : std::integral_constant<bool, has_join<F, V>::value || has_init<F, V>::value || has_final<F, V>::value> {};
+template <class F, class V, class Tag>
+struct brings_reduction_members<F, V, Tag, false>
+    : std::integral_constant<bool, has_join<F, V>::value || has_init<F, V>::value || has_final<F, V>::value || has_tagged_join<Tag, F, V>::value ||
+                                       has_tagged_init<Tag, F, V>::value || has_tagged_final<Tag, F, V>::value> {};
+
 // Uniform init/join/final over "functor with optional members" (default: value-init and operator+=,
 // FunctorAnalysis.hpp:604-613,724-732) -- the reducer used when the result argument is a plain scalar or View.
 template <class F, class V, class Tag>
@@ -56,7 +71,9 @@ struct FunctorReducer {
   using value_type = V;
   F f;
   KB200_FORCEINLINE_FUNCTION void init(V& v) const {
-    if constexpr (has_init<F, V>::value) f.init(v); else v = V();
+    if constexpr (!std::is_void<Tag>::value && has_tagged_init<Tag, F, V>::value) f.init(Tag{}, v);
+    else if constexpr (has_init<F, V>::value) f.init(v);
+    else v = V();
   }
   KB200_FORCEINLINE_FUNCTION void join(V& d, const V& s) const {
     if constexpr (!std::is_void<Tag>::value && has_tagged_join<Tag, F, V>::value) f.join(Tag{}, d, s);
@@ -64,7 +81,8 @@ struct FunctorReducer {
     else d += s;
   }
   KB200_FORCEINLINE_FUNCTION void final(V& v) const {
-    if constexpr (has_final<F, V>::value) f.final(v);
+    if constexpr (!std::is_void<Tag>::value && has_tagged_final<Tag, F, V>::value) f.final(Tag{}, v);
+    else if constexpr (has_final<F, V>::value) f.final(v);
   }
 };
 // plain-old-data fast case: no functor copy inside the reducer, and redux.sync for 32-bit integers
@@ -187,10 +205,76 @@ template <class... P> struct is_policy<RangePolicy<P...>> : std::true_type {};
 template <class... P> struct is_policy<MDRangePolicy<P...>> : std::true_type {};
 template <class... P> struct is_policy<TeamPolicy<P...>> : std::true_type {};
 
+// ---- runtime-length array reductions: functor::value_type = T[] + value_count (row a4) -----------------------------------
+template <class F, class = void> struct is_array_reduce_functor : std::false_type {};
+template <class F>
+struct is_array_reduce_functor<F, std::void_t<typename F::value_type>>
+    : std::integral_constant<bool, std::is_array<typename F::value_type>::value && std::extent<typename F::value_type>::value == 0> {};
+
+template <class T, class Tag, class F, class... P, int CAP>
+int array_reduce_launch(const RangePolicy<P...>& policy, const F& f, int count, T* rh, T* rd, std::integral_constant<int, CAP>) {
+  using Index = typename RangePolicy<P...>::index_type;
+  constexpr int BLOCK = 256;
+  b200_instance* inst = policy.space().impl_instance();
+  HostRuntime rt(inst);
+  const int64 n = (int64)(policy.end() - policy.begin()) > 0 ? (int64)(policy.end() - policy.begin()) : 0;
+  auto k = array_range_reduce_kernel<F, Tag, Index, T, CAP, BLOCK>;
+  int bps = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, BLOCK, 0);
+  if (bps < 1) bps = 1;
+  const int64 blocks = (n + BLOCK - 1) / BLOCK, cap = (int64)rt.sm_count() * bps;
+  const int grid = (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+  return array_reduce_run<T>(inst, count, grid, rh, rd, [&](T* partials, unsigned* ticket, T* dst) {
+    k<<<grid, BLOCK, 0, rt.stream()>>>(f, policy.begin(), n, count, partials, ticket, dst);
+  });
+}
+template <class T, class Tag, class F, class... P, int CAP>
+int array_reduce_launch(const MDRangePolicy<P...>& policy, const F& f, int count, T* rh, T* rd, std::integral_constant<int, CAP>) {
+  using Policy = MDRangePolicy<P...>;
+  using Index = typename Policy::index_type;
+  b200_instance* inst = policy.space().impl_instance();
+  HostRuntime rt(inst);
+  MDLaunchShape<Policy> sh(policy);
+  auto k = array_mdrange_reduce_kernel<F, Tag, T, CAP, Policy::rank, Index>;
+  int bps = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, sh.threads, 0);
+  if (bps < 1) bps = 1;
+  const long long cap = (long long)rt.sm_count() * bps, tiles = sh.p.num_tiles;
+  const int grid = (int)(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
+  sh.set_grid(grid);
+  if (tiles < 1) { sh.p.num_tiles = 0; sh.block = dim3(32, 1, 1); }
+  return array_reduce_run<T>(inst, count, grid, rh, rd, [&](T* partials, unsigned* ticket, T* dst) {
+    k<<<grid, sh.block, 0, rt.stream()>>>(f, sh.p, count, partials, ticket, dst);
+  });
+}
+template <class Policy, class F, class R>
+void array_reduce_entry(const Policy& policy, const F& f, R&& result) {
+  using T = std::remove_extent_t<typename F::value_type>;
+  using Tag = typename Policy::work_tag;
+  using RD = std::decay_t<R>;
+  const int count = (int)f.value_count;
+  T *rh = nullptr, *rd = nullptr;
+  if constexpr (is_view_v<RD>) {
+    if ((int)result.size() < count) throw std::runtime_error("kb200::parallel_reduce(value_type[]): result View is shorter than value_count");
+    if (RD::is_device) rd = (T*)result.data(); else rh = (T*)result.data();
+  } else {
+    rh = &result[0];  // C array or pointer on the host
+  }
+  int rc;
+  if (count <= 8) rc = array_reduce_launch<T, Tag>(policy, f, count, rh, rd, std::integral_constant<int, 8>{});
+  else if (count <= 32) rc = array_reduce_launch<T, Tag>(policy, f, count, rh, rd, std::integral_constant<int, 32>{});
+  else rc = array_reduce_launch<T, Tag>(policy, f, count, rh, rd, std::integral_constant<int, 64>{});
+  throw_on_error(rc);
+}
+
 template <class Policy, class F, class R>
 void reduce_entry(const Policy& policy, const F& f, R&& result) {
   using RD = std::decay_t<R>;
   using Tag = typename Policy::work_tag;
+  if constexpr (is_array_reduce_functor<F>::value) {
+    array_reduce_entry(policy, f, static_cast<R&&>(result));
+    return;
+  } else
   if constexpr (is_reducer_v<RD>) {
     using V = typename RD::value_type;
     ReducerAdapter<RD> red{result};
@@ -200,7 +284,7 @@ void reduce_entry(const Policy& policy, const F& f, R&& result) {
   } else if constexpr (is_view_v<RD>) {
     using V = typename RD::non_const_value_type;
     static_assert(RD::rank == 0, "parallel_reduce: View results must be rank 0 (array reductions are not on this path)");
-    if constexpr (has_join<F, V>::value || has_init<F, V>::value || has_final<F, V>::value) {
+    if constexpr (brings_reduction_members<F, V, Tag>::value) {
       reduce_dispatch(policy, f, FunctorReducer<F, V, Tag>{f}, target_of_view(result));
     } else {
       reduce_dispatch(policy, f, DefaultSumReducer<V>{}, target_of_view(result));
@@ -208,7 +292,7 @@ void reduce_entry(const Policy& policy, const F& f, R&& result) {
   } else {
     using V = RD;
     static_assert(!std::is_const<std::remove_reference_t<R>>::value, "parallel_reduce: result must be a non-const reference");
-    if constexpr (has_join<F, V>::value || has_init<F, V>::value || has_final<F, V>::value) {
+    if constexpr (brings_reduction_members<F, V, Tag>::value) {
       reduce_dispatch(policy, f, FunctorReducer<F, V, Tag>{f}, target_of_scalar(result));
     } else {
       reduce_dispatch(policy, f, DefaultSumReducer<V>{}, target_of_scalar(result));
