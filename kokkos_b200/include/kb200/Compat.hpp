@@ -57,9 +57,30 @@ KB200_INLINE_FUNCTION void abort(const char* msg) {
 #endif
 }
 
-struct ParallelForTag {};     // core/src/Kokkos_Core_fwd.hpp: pattern tags for team_size_max / team_size_recommended
-struct ParallelReduceTag {};
-struct ParallelScanTag {};
+// Host-side tag type: enough for create_mirror_view_and_copy(DefaultHostExecutionSpace(), view) and memory_space queries.
+// It is NOT an execution space that can run patterns (this package has no host backend by design).
+struct DefaultHostExecutionSpace {
+  using execution_space = DefaultHostExecutionSpace;
+  using memory_space = HostSpace;
+  using device_type = Device<DefaultHostExecutionSpace, HostSpace>;
+  static const char* name() { return "HostTag"; }
+  void fence(const std::string& = "") const {}
+};
+
+// device-wide memory fence (core/src/Kokkos_Atomics_Desul_Wrapper.hpp: Kokkos::memory_fence)
+KB200_FORCEINLINE_FUNCTION void memory_fence() {
+#ifdef __CUDA_ARCH__
+  __threadfence();
+#else
+  __atomic_thread_fence(__ATOMIC_SEQ_CST);
+#endif
+}
+
+namespace numbers {  // core/src/Kokkos_MathematicalConstants.hpp
+inline constexpr double pi = 3.141592653589793238462643383279502884;
+inline constexpr double e = 2.718281828459045235360287471352662498;
+inline constexpr double sqrt2 = 1.414213562373095048801688724209698079;
+}  // namespace numbers
 
 // Kokkos::printf (core/src/Kokkos_Printf.hpp): callable from host and device code
 template <class... Args>

@@ -16,6 +16,13 @@
 #define KB200_LAMBDA [=] __host__ __device__
 #define KB200_CLASS_LAMBDA [ =, *this ] __host__ __device__
 
+// namespace name as it appears in diagnostics (the layer is declared as `Kokkos` in KB200_AS_KOKKOS mode)
+#ifdef KB200_AS_KOKKOS
+#define KB200_NS_STR "Kokkos"
+#else
+#define KB200_NS_STR "kb200"
+#endif
+
 #include <cstdint>
 #include <cstddef>
 

@@ -15,6 +15,9 @@
 
 #include "B200.hpp"
 #include <array>
+#include <cstring>
+#include <limits>
+#include <string>
 #include <initializer_list>
 #include <type_traits>
 
@@ -33,6 +36,10 @@ constexpr AUTO_t AUTO{};
 enum class Iterate { Default, Left, Right };
 template <unsigned N, Iterate OuterDir = Iterate::Default, Iterate InnerDir = Iterate::Default>
 struct Rank { static constexpr int rank = (int)N; static constexpr Iterate outer_direction = OuterDir, inner_direction = InnerDir; };
+
+struct ParallelForTag {};     // core/src/Kokkos_Core_fwd.hpp: pattern tags for team_size_max / team_size_recommended
+struct ParallelReduceTag {};
+struct ParallelScanTag {};
 
 namespace Impl {
 template <class T> struct is_schedule : std::false_type {};
@@ -65,8 +72,13 @@ struct policy_traits<F, R...> {
 template <class IT> struct index_of { using type = typename IT::type; };
 template <> struct index_of<void> { using type = long long; };
 
+// defined in Team.hpp, after the team kernels
+template <class Policy, class F, class PatternTag>
+int team_size_limit(const Policy& pol, const F& f, const PatternTag&);
+
 [[noreturn]] inline void policy_abort(const char* msg) {
-  std::fprintf(stderr, "%s\n", msg);
+  std::fprintf(stderr, "%s", msg);
+  if (msg[0] && msg[std::strlen(msg) - 1] != '\n') std::fprintf(stderr, "\n");
   std::abort();
 }
 }  // namespace Impl
@@ -86,10 +98,18 @@ class RangePolicy {
   using member_type = index_type;
 
   RangePolicy() : m_begin(0), m_end(0) {}
-  RangePolicy(index_type b, index_type e) : m_begin(b), m_end(e) { check(); }
-  RangePolicy(const B200& s, index_type b, index_type e) : m_space(s), m_begin(b), m_end(e) { check(); }
-  RangePolicy(index_type b, index_type e, ChunkSize c) : m_begin(b), m_end(e), m_chunk(c.value) { check(); }
-  RangePolicy(const B200& s, index_type b, index_type e, ChunkSize c) : m_space(s), m_begin(b), m_end(e), m_chunk(c.value) { check(); }
+  // bounds of any integral type: each is checked for a value-preserving conversion to index_type before use
+  // (core/src/Kokkos_ExecPolicy.hpp:235-290; core/unit_test/TestRangePolicyConstructors.hpp pins the diagnostics)
+  template <class B, class E, class = std::enable_if_t<std::is_convertible<B, index_type>::value && std::is_convertible<E, index_type>::value &&
+                                                       !std::is_same<std::decay_t<B>, B200>::value>>
+  RangePolicy(const B b, const E e) : m_begin(checked(b)), m_end(checked(e)) { check(); }
+  template <class B, class E, class = std::enable_if_t<std::is_convertible<B, index_type>::value && std::is_convertible<E, index_type>::value>>
+  RangePolicy(const B200& s, const B b, const E e) : m_space(s), m_begin(checked(b)), m_end(checked(e)) { check(); }
+  template <class B, class E, class = std::enable_if_t<std::is_convertible<B, index_type>::value && std::is_convertible<E, index_type>::value &&
+                                                       !std::is_same<std::decay_t<B>, B200>::value>>
+  RangePolicy(const B b, const E e, ChunkSize c) : m_begin(checked(b)), m_end(checked(e)), m_chunk(c.value) { check(); }
+  template <class B, class E, class = std::enable_if_t<std::is_convertible<B, index_type>::value && std::is_convertible<E, index_type>::value>>
+  RangePolicy(const B200& s, const B b, const E e, ChunkSize c) : m_space(s), m_begin(checked(b)), m_end(checked(e)), m_chunk(c.value) { check(); }
 
   const B200& space() const { return m_space; }
   KB200_INLINE_FUNCTION index_type begin() const { return m_begin; }
@@ -99,7 +119,28 @@ class RangePolicy {
 
  private:
   void check() {
-    if (m_end < m_begin) Impl::policy_abort("kb200::RangePolicy bounds error: The lower bound is greater than the upper bound");
+    if (m_end < m_begin) {
+      const std::string msg = std::string(KB200_NS_STR "::RangePolicy bounds error: The lower bound (") + std::to_string(m_begin) +
+                              ") is greater than the upper bound (" + std::to_string(m_end) + ").\n";
+      Impl::policy_abort(msg.c_str());
+    }
+  }
+  template <class T>
+  static index_type checked(const T bound) {
+    if constexpr (std::is_convertible<index_type, T>::value) {
+      bool unsafe = false;
+      if constexpr (std::is_arithmetic<T>::value && std::is_signed<T>::value != std::is_signed<index_type>::value) {
+        if constexpr (std::is_signed<T>::value) unsafe = unsafe || bound < static_cast<T>(std::numeric_limits<index_type>::min());
+        if constexpr (std::is_signed<index_type>::value) unsafe = unsafe || bound > static_cast<T>(std::numeric_limits<index_type>::max());
+      }
+      unsafe = unsafe || static_cast<T>(static_cast<index_type>(bound)) != bound;  // narrowing
+      if (unsafe) {
+        const std::string msg = std::string(KB200_NS_STR "::RangePolicy bound type error: an unsafe implicit conversion is performed on a bound (") +
+                                std::to_string(bound) + "), which may not preserve its original value.\n";
+        Impl::policy_abort(msg.c_str());
+      }
+    }
+    return static_cast<index_type>(bound);
   }
   B200 m_space;
   index_type m_begin, m_end;
@@ -223,16 +264,26 @@ class TeamPolicy {
   TeamPolicy& set_scratch_size(int level, PerThreadValue t) { chk_level(level); m_thread_scratch[level] = t.value; return *this; }
   TeamPolicy& set_scratch_size(int level, PerTeamValue a, PerThreadValue b) { chk_level(level); m_team_scratch[level] = a.value; m_thread_scratch[level] = b.value; return *this; }
   TeamPolicy& set_scratch_size(int level, PerThreadValue b, PerTeamValue a) { return set_scratch_size(level, a, b); }
-  // team_size_max / team_size_recommended (Cuda_Parallel_Team.hpp:96-172): 1024-thread blocks, a multiple of a warp
-  template <class F, class Tag> int team_size_max(const F&, const Tag&) const { return 1024 / (m_vec > 0 ? m_vec : 1); }
-  template <class F, class Tag> int team_size_recommended(const F&, const Tag&) const { return impl_default_team_size(); }
+  // team_size_max / team_size_recommended (Cuda_Parallel_Team.hpp:96-172,346-389): derived from the attributes of the kernel
+  // that would actually be launched for this functor (registers, launch bounds) and from the level-0 scratch request
+  template <class F, class PatternTag> int team_size_max(const F& f, const PatternTag& t) const { return Impl::team_size_limit(*this, f, t); }
+  template <class F, class PatternTag> int team_size_recommended(const F& f, const PatternTag& t) const {
+    const int mx = Impl::team_size_limit(*this, f, t), dflt = impl_default_team_size();
+    return dflt < mx ? dflt : mx;
+  }
+  // reducer-taking forms (Kokkos_ExecPolicy.hpp:365-508)
+  template <class F, class R> int team_size_max(const F& f, const R&, const ParallelReduceTag& t) const { return Impl::team_size_limit(*this, f, t); }
+  template <class F, class R> int team_size_recommended(const F& f, const R&, const ParallelReduceTag& t) const { return team_size_recommended(f, t); }
   int impl_default_team_size() const { const int v = m_vec > 0 ? m_vec : 1; return 256 / v > 0 ? 256 / v : 1; }
 
  private:
   void chk_level(int level) const { if (level < 0 || level > 1) Impl::policy_abort("kb200::TeamPolicy: scratch level must be 0 or 1"); }
   void check() {
     if (m_league < 0) Impl::policy_abort("kb200::TeamPolicy: negative league size");
-    if (m_vec > 32 || (m_vec > 0 && (m_vec & (m_vec - 1)))) Impl::policy_abort("kb200::TeamPolicy: vector length must be a power of two <= 32");
+    // as the reference's Cuda backend: clamp the request to 32 and round it DOWN to a power of two
+    // (Cuda/Kokkos_Cuda_Parallel_Team.hpp verify_requested_vector_length; TestTeamVector.hpp:1037 asks for 33 and 19)
+    if (m_vec > 32) m_vec = 32;
+    if (m_vec > 0) { int p2 = 1; while (p2 * 2 <= m_vec) p2 *= 2; m_vec = p2; }
     if (m_team > 0 && m_vec > 0 && m_team * m_vec > 1024) throw std::runtime_error("kb200::TeamPolicy: requested team_size * vector_length exceeds 1024 threads");
   }
   B200 m_space;

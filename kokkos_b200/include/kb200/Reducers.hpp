@@ -28,6 +28,8 @@ namespace kb200 {
 
 struct B200Space;  // device memory space tag (View.hpp)
 struct HostSpace;
+template <class DataType, class... Props>
+class View;
 
 // ---------------------------------------------------------------- identities
 template <class T, class Enable = void>
@@ -109,6 +111,7 @@ struct ReducerBase {
 #define KB200_REDUCER_HEAD(Name, ...)                         \
   using reducer = Name;                                       \
   using value_type = __VA_ARGS__;                             \
+  using result_view_type = View<__VA_ARGS__, Space>;          \
   using Base = Impl::ReducerBase<__VA_ARGS__>;                \
   using Base::Base;
 

@@ -69,34 +69,48 @@ class ScratchMemorySpace {
   using is_scratch_tag = void;
   using memory_space = ScratchMemorySpace;
   using execution_space = ExecSpace;
+  using device_type = Device<ExecSpace, ScratchMemorySpace>;
+  using array_layout = LayoutLeft;
+  using size_type = unsigned int;
   static constexpr int ALIGN = 8;  // Kokkos_ScratchSpace.hpp:44
 
-  KB200_INLINE_FUNCTION ScratchMemorySpace() : m_iter{nullptr, nullptr}, m_end{nullptr, nullptr}, m_default_level(0) {}
+  KB200_INLINE_FUNCTION ScratchMemorySpace() : m_iter{nullptr, nullptr}, m_end{nullptr, nullptr}, m_mult(1), m_slot(0), m_default_level(0) {}
   KB200_INLINE_FUNCTION ScratchMemorySpace(void* p0, size_t s0, void* p1, size_t s1)
-      : m_iter{(char*)p0, (char*)p1}, m_end{(char*)p0 + s0, (char*)p1 + s1}, m_default_level(0) {}
+      : m_iter{(char*)p0, (char*)p1}, m_end{(char*)p0 + s0, (char*)p1 + s1}, m_mult(1), m_slot(0), m_default_level(0) {}
 
   template <class IntType>
-  KB200_INLINE_FUNCTION void* get_shmem(const IntType& size, int level = -1) const { return get_shmem_common(size, ALIGN, level); }
+  KB200_INLINE_FUNCTION void* get_shmem(const IntType& size, int level = -1) const { return carve((size_t)size, 1, level); }
   template <class IntType>
   KB200_INLINE_FUNCTION void* get_shmem_aligned(const IntType& size, const ptrdiff_t alignment, int level = -1) const {
-    return get_shmem_common(size, alignment, level);
+    return carve((size_t)size, (size_t)alignment, level);
+  }
+  // One pool per level (Kokkos_ScratchSpace.hpp:95-170): a TEAM request of `size` takes `size` bytes and every thread gets the
+  // same pointer; a THREAD request takes size x team_size bytes and thread r gets the r-th slice.  The handle returned by
+  // team_scratch()/thread_scratch() is this one object switched between the two modes, so successive requests advance
+  // the same cursor and nullptr is returned once the pool is exhausted.
+  KB200_INLINE_FUNCTION const ScratchMemorySpace& impl_set_mode(int level, int multiplier, int slot) const {
+    m_default_level = level; m_mult = multiplier; m_slot = slot;
+    return *this;
   }
   KB200_INLINE_FUNCTION ScratchMemorySpace set_level(int level) const { ScratchMemorySpace s(*this); s.m_default_level = level; return s; }
 
  private:
-  template <class IntType>
-  KB200_INLINE_FUNCTION void* get_shmem_common(const IntType& size, const ptrdiff_t alignment, int level) const {
+  KB200_INLINE_FUNCTION void* carve(size_t size, size_t alignment, int level) const {
     if (level == -1) level = m_default_level;
-    char*& it = m_iter[level];
-    const uintptr_t mis = reinterpret_cast<uintptr_t>(it) % alignment;
-    char* p = it + (mis ? alignment - mis : 0);
-    if (p + size > m_end[level]) return nullptr;  // out of scratch: nullptr, as the reference
-    it = p + size;
-    return p;
+    char* cur = m_iter[level];
+    if (alignment > 1) {
+      const size_t mis = reinterpret_cast<uintptr_t>(cur) % alignment;
+      if (mis) cur += alignment - mis;
+    }
+    const size_t need = size * (size_t)m_mult;
+    if (cur > m_end[level] || need > (size_t)(m_end[level] - cur)) return nullptr;  // pool exhausted: cursor unchanged
+    m_iter[level] = cur + need;
+    return cur + (size_t)m_slot * size;
   }
   mutable char* m_iter[2];
   char* m_end[2];
-  int m_default_level;
+  mutable int m_mult, m_slot;
+  mutable int m_default_level;
 };
 
 // ------------------------------------------------------------------------------------------ team handle
@@ -108,7 +122,8 @@ class B200TeamMember {
   KB200_TEAM_FUNCTION B200TeamMember(void* collective_smem, void* l0, size_t l0_team, size_t l0_thread, void* l1, size_t l1_team,
                                        size_t l1_thread, int league_rank, int league_size)
       : m_collective(collective_smem), m_l0((char*)l0), m_l1((char*)l1), m_l0_team(l0_team), m_l0_thread(l0_thread),
-        m_l1_team(l1_team), m_l1_thread(l1_thread), m_league_rank(league_rank), m_league_size(league_size) {}
+        m_l1_team(l1_team), m_l1_thread(l1_thread), m_league_rank(league_rank), m_league_size(league_size),
+        m_scr(l0, l0_team + l0_thread * (size_t)Impl::tm::ny(), l1, l1_team + l1_thread * (size_t)Impl::tm::ny()) {}
 
   KB200_TEAM_FUNCTION int league_rank() const { return m_league_rank; }
   KB200_TEAM_FUNCTION int league_size() const { return m_league_size; }
@@ -118,14 +133,12 @@ class B200TeamMember {
   KB200_TEAM_FUNCTION int impl_vector_length() const { return Impl::tm::nx(); }
   KB200_TEAM_FUNCTION void team_barrier() const { Impl::tm::sync(); }
 
-  // scratch handles (a fresh bump allocator per call, as in Cuda_Team.hpp:86-101)
-  KB200_TEAM_FUNCTION scratch_memory_space team_shmem() const { return team_scratch(0); }
-  KB200_TEAM_FUNCTION scratch_memory_space team_scratch(int level) const {
-    return scratch_memory_space(m_l0, m_l0_team, m_l1, m_l1_team).set_level(level);
-  }
-  KB200_TEAM_FUNCTION scratch_memory_space thread_scratch(int level) const {
-    return scratch_memory_space(m_l0 + m_l0_team + m_l0_thread * Impl::tm::ty(), m_l0_thread,
-                                m_l1 + m_l1_team + m_l1_thread * Impl::tm::ty(), m_l1_thread).set_level(level);
+  // scratch handles: ONE pool per level whose cursor lives in the member (Cuda_Team.hpp:86-101 returns the member's scratch
+  // space switched to team or thread mode); TestTeamBasic.hpp:165-180 and TestTeam.hpp:920-1036,1130-1180 pin the behaviour
+  KB200_TEAM_FUNCTION const scratch_memory_space& team_shmem() const { return team_scratch(0); }
+  KB200_TEAM_FUNCTION const scratch_memory_space& team_scratch(int level) const { return m_scr.impl_set_mode(level, 1, 0); }
+  KB200_TEAM_FUNCTION const scratch_memory_space& thread_scratch(int level) const {
+    return m_scr.impl_set_mode(level, Impl::tm::ny(), Impl::tm::ty());
   }
 
   // ---- team collectives (all threads of the team must call) ----
@@ -190,6 +203,7 @@ class B200TeamMember {
   char *m_l0, *m_l1;
   size_t m_l0_team, m_l0_thread, m_l1_team, m_l1_thread;
   int m_league_rank, m_league_size;
+  scratch_memory_space m_scr;  // both levels; cursor state is mutable inside
 };
 
 // ------------------------------------------------------------------------------------------ nested policies
@@ -315,25 +329,51 @@ KB200_TEAM_FUNCTION void parallel_reduce(const Impl::TeamVectorRangeStruct<I>& r
   }
 }
 
-// ---- nested parallel_scan (sum semantics, f(i, partial, final)); ThreadVectorRange and TeamThreadRange
+// ---- nested parallel_scan, f(i, partial, final); ThreadVectorRange and TeamThreadRange
+//      forms: (range, f)  sum;  (range, f, return_value)  sum + total;  (range, f, reducer)  the reducer's init/join, total in
+//      reducer.reference()   (core/src/Cuda/Kokkos_Cuda_Team.hpp:844-1070)
+namespace Impl {
+// scan over the vector lanes of one thread with an arbitrary (ordered) join; returns the total in every lane
+template <class I, class L, class V, class Red>
+KB200_TEAM_FUNCTION V vector_scan(const ThreadVectorRangeStruct<I>& r, const L& f, const Red& red) {
+  const int vl = tm::nx();
+  const int lane = (tm::tx() + tm::nx() * tm::ty()) & 31;
+  V carry;
+  red.init(carry);
+  for (I base = r.begin; base < r.end; base += (I)vl) {
+    const I i = base + (I)tm::tx();
+    V c;
+    red.init(c);
+    if (i < r.end) f(i, c, false);
+    V incl = c;  // inclusive scan over the group, lower lanes on the left
+    for (int d = 1; d < vl; d <<= 1) {
+      V lo = tm::up(incl, d);
+      if (tm::tx() >= d) { red.join(lo, incl); incl = lo; }
+    }
+    V ex = carry;  // exclusive prefix = carry (+) inclusive prefix of the lane before me
+    V prev = tm::up(incl, 1);
+    if (tm::tx() > 0) red.join(ex, prev);
+    if (i < r.end) f(i, ex, true);
+    V last = tm::idx(incl, lane - tm::tx() + vl - 1);
+    red.join(carry, last);
+  }
+  return carry;
+}
+}  // namespace Impl
 template <class I, class L>
 KB200_TEAM_FUNCTION void parallel_scan(const Impl::ThreadVectorRangeStruct<I>& r, const L& f) {
   using V = std::remove_reference_t<typename Impl::scan_arg_of<L, I>::type>;
-  const int vl = Impl::tm::nx();
-  const int lane = (Impl::tm::tx() + Impl::tm::nx() * Impl::tm::ty()) & 31;
-  V carry = V();
-  for (I base = r.begin; base < r.end; base += (I)vl) {
-    const I i = base + (I)Impl::tm::tx();
-    V c = V();
-    if (i < r.end) f(i, c, false);
-    V incl = c;  // inclusive scan over the group
-    for (int d = 1; d < vl; d <<= 1) {
-      V lo = Impl::tm::up(incl, d);
-      if (Impl::tm::tx() >= d) incl += lo;
-    }
-    V ex = carry + (incl - c);
-    if (i < r.end) f(i, ex, true);
-    carry += Impl::tm::idx(incl, lane - Impl::tm::tx() + vl - 1);
+  (void)Impl::vector_scan<I, L, V>(r, f, Impl::NestedSum<V>{});
+}
+template <class I, class L, class R>
+KB200_TEAM_FUNCTION void parallel_scan(const Impl::ThreadVectorRangeStruct<I>& r, const L& f, R&& result) {
+  using RD = std::decay_t<R>;
+  if constexpr (is_reducer_v<RD>) {
+    using V = typename RD::value_type;
+    const V total = Impl::vector_scan<I, L, V>(r, f, Impl::ReducerAdapter<RD>{result});
+    result.reference() = total;
+  } else {
+    result = Impl::vector_scan<I, L, RD>(r, f, Impl::NestedSum<RD>{});
   }
 }
 template <class I, class L>
@@ -351,6 +391,22 @@ KB200_TEAM_FUNCTION void parallel_scan(const Impl::TeamThreadRangeStruct<I>& r, 
     r.member.team_reduce(Impl::NestedSum<V>{}, tot);
     carry += tot;
   }
+}
+template <class I, class L, class V>
+KB200_TEAM_FUNCTION void parallel_scan(const Impl::TeamThreadRangeStruct<I>& r, const L& f, V& result) {
+  V carry = V();
+  const I ts = (I)Impl::tm::ny();
+  for (I base = r.begin; base < r.end; base += ts) {
+    const I i = base + (I)Impl::tm::ty();
+    V c = V();
+    if (i < r.end) f(i, c, false);
+    V ex = carry + r.member.team_scan(c);
+    if (i < r.end) f(i, ex, true);
+    V tot = c;
+    r.member.team_reduce(Impl::NestedSum<V>{}, tot);
+    carry += tot;
+  }
+  result = carry;
 }
 
 // ---- single
@@ -423,14 +479,27 @@ struct TeamShape {
   int team, vec, threads, grid;
   size_t smem;
   TeamLaunchParams p;
-  int setup(const Policy& pol, const void* kernel, size_t value_bytes) {
+  // level-0 scratch a functor asks for itself: team_shmem_size(team_size) / shmem_size(team_size)
+  // (core/src/impl/Kokkos_FunctorAnalysis.hpp FunctorTeamShmemSize; used by core/unit_test/TestTeamVector.hpp:460-463)
+  template <class F, class = void> struct has_team_shmem_size : std::false_type {};
+  template <class F> struct has_team_shmem_size<F, std::void_t<decltype(std::declval<const F&>().team_shmem_size(0))>> : std::true_type {};
+  template <class F, class = void> struct has_shmem_size : std::false_type {};
+  template <class F> struct has_shmem_size<F, std::void_t<decltype(std::declval<const F&>().shmem_size(0))>> : std::true_type {};
+  template <class F>
+  static size_t functor_shmem(const F& f, int team_size) {
+    if constexpr (has_team_shmem_size<F>::value) return (size_t)f.team_shmem_size(team_size);
+    else if constexpr (has_shmem_size<F>::value) return (size_t)f.shmem_size(team_size);
+    else return 0;
+  }
+  template <class F>
+  int setup(const Policy& pol, const void* kernel, size_t value_bytes, const F& f) {
     HostRuntime rt(pol.space().impl_instance());
     vec = pol.impl_auto_vector_length() ? 1 : pol.impl_vector_length();
     team = pol.impl_auto_team_size() ? (256 / vec > 0 ? 256 / vec : 1) : pol.team_size();
     threads = team * vec;
     if (threads > 1024) throw std::runtime_error("kb200::TeamPolicy: team_size * vector_length exceeds 1024");
     p.league_size = pol.league_size();
-    p.l0_team = pol.team_scratch_size(0); p.l0_thread = pol.thread_scratch_size(0);
+    p.l0_team = pol.team_scratch_size(0) + functor_shmem(f, team); p.l0_thread = pol.thread_scratch_size(0);
     p.l1_team = pol.team_scratch_size(1); p.l1_thread = pol.thread_scratch_size(1);
     const size_t l0 = p.l0_team + p.l0_thread * team;
     size_t coll = kTeamCollectiveBytes;
@@ -457,13 +526,64 @@ struct TeamShape {
 };
 }  // namespace Impl
 
+namespace Impl {
+// value type of a TeamPolicy reduction functor without a result argument at hand: F::value_type, else the last parameter
+// of its (non-template) call operator
+template <class F, class = void>
+struct team_reduce_value_of {
+  template <class C, class R, class A0, class A1> static std::remove_reference_t<A1> pick(R (C::*)(A0, A1) const);
+  template <class C, class R, class T, class A0, class A1> static std::remove_reference_t<A1> pick(R (C::*)(T, A0, A1) const);
+  using type = decltype(pick(&F::operator()));
+};
+template <class F>
+struct team_reduce_value_of<F, std::void_t<typename F::value_type>> { using type = typename F::value_type; };
+template <class F, class = void> struct team_reduce_value_known : std::false_type {};
+template <class F> struct team_reduce_value_known<F, std::void_t<typename team_reduce_value_of<F>::type>> : std::true_type {};
+
+template <class Policy, class F, class PatternTag>
+int team_size_limit(const Policy& pol, const F& f, const PatternTag&) {
+  using Tag = typename Policy::work_tag;
+  const int vec = pol.impl_vector_length() > 0 ? pol.impl_vector_length() : 1;
+  cudaFuncAttributes attr{};
+  size_t value_bytes = 16;
+  bool halve = false;
+  if constexpr (std::is_same<PatternTag, ParallelReduceTag>::value) {
+    if constexpr (team_reduce_value_known<F>::value) {
+      using V = typename team_reduce_value_of<F>::type;
+      value_bytes = sizeof(V);
+      throw_on_error(b200_report_error((int)cudaFuncGetAttributes(&attr, team_reduce_kernel<F, Tag, DefaultSumReducer<V>>), "kb200::team_size_max"));
+    } else {  // value type only known with the result argument: bound it by the for-kernel of the same functor, halved
+      attr.maxThreadsPerBlock = 1024;
+      halve = true;
+    }
+  } else {
+    throw_on_error(b200_report_error((int)cudaFuncGetAttributes(&attr, team_for_kernel<F, Tag>), "kb200::team_size_max"));
+  }
+  int max_threads = attr.maxThreadsPerBlock > 0 ? attr.maxThreadsPerBlock : 1024;
+  if (halve) max_threads /= 2;
+  constexpr unsigned lb = Policy::launch_bounds::maxTperB;
+  if (lb > 0 && (int)lb < max_threads) max_threads = (int)lb;
+  int team = max_threads / vec;
+  // level-0 scratch (policy request + what the functor asks for itself) must fit next to the collective area
+  while (team > 1) {
+    size_t coll = kTeamCollectiveBytes;
+    if (value_bytes * 34 > coll) coll = value_bytes * 34;
+    const size_t l0 = pol.team_scratch_size(0) + TeamShape<Policy>::functor_shmem(f, team) + pol.thread_scratch_size(0) * (size_t)team;
+    if (coll + l0 + 16 <= (size_t)220 * 1024) break;
+    team /= 2;
+  }
+  if (team * vec >= 32) team = (team * vec / 32) * 32 / vec;  // whole warps
+  return team > 0 ? team : 1;
+}
+}  // namespace Impl
+
 template <class... P, class F>
 void parallel_for(const std::string& /*label*/, const TeamPolicy<P...>& pol, const F& f) {
   using Tag = typename TeamPolicy<P...>::work_tag;
   if (pol.league_size() <= 0) return;
   auto k = Impl::team_for_kernel<F, Tag>;
   Impl::TeamShape<TeamPolicy<P...>> sh;
-  Impl::throw_on_error(sh.setup(pol, (const void*)k, 16));
+  Impl::throw_on_error(sh.setup(pol, (const void*)k, 16, f));
   Impl::HostRuntime rt(pol.space().impl_instance());
   k<<<sh.grid, dim3(sh.vec, sh.team, 1), sh.smem, rt.stream()>>>(f, sh.p);
   Impl::throw_on_error(rt.check_launch("kb200::team_for_kernel"));
@@ -478,7 +598,7 @@ void reduce_dispatch(const TeamPolicy<P...>& pol, const F& f, const Red& red, Re
   using V = typename Red::value_type;
   auto k = team_reduce_kernel<F, Tag, Red>;
   TeamShape<TeamPolicy<P...>> sh;
-  throw_on_error(sh.setup(pol, (const void*)k, sizeof(V)));
+  throw_on_error(sh.setup(pol, (const void*)k, sizeof(V), f));
   HostRuntime rt(pol.space().impl_instance());
   ReduceScratch s;
   void *slot_dev = nullptr, *slot_host = nullptr;

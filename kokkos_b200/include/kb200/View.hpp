@@ -23,6 +23,23 @@ namespace kb200 {
 
 struct LayoutLeft {};
 struct LayoutRight {};
+// LayoutStride: only the extent bookkeeping used for scratch sizing (View<..., LayoutStride>::shmem_size(order_dimensions(...)),
+// core/src/Kokkos_Layout.hpp:148-230); strided element access is outside the hot path
+struct LayoutStride {
+  size_t dimension[8] = {1, 1, 1, 1, 1, 1, 1, 1};
+  size_t stride[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  template <class IOrder, class IDim>
+  static LayoutStride order_dimensions(int rank, const IOrder* order, const IDim* dims) {
+    LayoutStride l;
+    size_t n = 1;
+    for (int r = 0; r < rank; ++r) {
+      l.stride[order[r]] = n;
+      l.dimension[order[r]] = (size_t)dims[order[r]];
+      n *= (size_t)dims[order[r]];
+    }
+    return l;
+  }
+};
 struct HostSpace {
   using memory_space = HostSpace;
   static constexpr const char* name() { return "Host"; }
@@ -61,6 +78,19 @@ struct AtomicDataElement;
 namespace Impl {
 template <class D> struct data_type_rank { static constexpr int value = 0; using type = D; };
 template <class D> struct data_type_rank<D*> { static constexpr int value = 1 + data_type_rank<D>::value; using type = typename data_type_rank<D>::type; };
+// static extents: double[100], double*[3] ... (dynamic dimensions first, as in Kokkos data types)
+template <class D, size_t N> struct data_type_rank<D[N]> { static constexpr int value = 1 + data_type_rank<D>::value; using type = typename data_type_rank<D>::type; };
+template <class D> struct data_type_dynamic_rank { static constexpr int value = 0; };
+template <class D> struct data_type_dynamic_rank<D*> { static constexpr int value = 1 + data_type_dynamic_rank<D>::value; };
+template <class D, size_t N> struct data_type_dynamic_rank<D[N]> { static constexpr int value = data_type_dynamic_rank<D>::value; };
+// static extent of dimension r (0 = dynamic); for D = T*..*[N1][N2] the static dimensions are the trailing ones, outermost first
+template <class D> struct data_type_static { static constexpr size_t get(int) { return 0; } };
+template <class D> struct data_type_static<D*> { static constexpr size_t get(int r) { return data_type_static<D>::get(r); } };
+template <class D, size_t N> struct data_type_static<D[N]> {
+  static constexpr size_t get(int r) {  // r counts static dimensions from the outermost
+    return r == 0 ? N : data_type_static<D>::get(r - 1);
+  }
+};
 
 template <class... P> struct view_props;
 template <> struct view_props<> {
@@ -140,10 +170,19 @@ class View {
   template <class S, class = typename S::is_scratch_tag>
   KB200_INLINE_FUNCTION View(const S& scratch, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) : m_rec(nullptr) {
     set_extents(n0, n1, n2, n3, n4, n5);
-    m_data = static_cast<pointer_type>(scratch.get_shmem_aligned(size() * sizeof(value_type), alignof(value_type) > 8 ? alignof(value_type) : 8));
+    m_data = static_cast<pointer_type>(scratch.get_shmem_aligned(size() * sizeof(value_type), (ptrdiff_t)scratch_value_alignment));
+  }
+  // scratch Views are aligned to max(sizeof(T), alignof(T), 8) and shmem_size() reserves that much slack
+  // (core/src/View/Kokkos_ViewMapping / Kokkos_View.hpp scratch_value_alignment; TestTeam.hpp:1601-1640 checks it)
+  static constexpr size_t scratch_value_alignment =
+      sizeof(value_type) > (alignof(value_type) > 8 ? alignof(value_type) : 8) ? sizeof(value_type) : (alignof(value_type) > 8 ? alignof(value_type) : 8);
+  static size_t shmem_size(const LayoutStride& l) {
+    size_t n = 1;
+    for (int r = 0; r < rank; ++r) n *= l.dimension[r];
+    return n * sizeof(value_type) + scratch_value_alignment;
   }
   static constexpr size_t shmem_size(size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) {
-    return (rank > 0 ? n0 : 1) * (rank > 1 ? n1 : 1) * (rank > 2 ? n2 : 1) * (rank > 3 ? n3 : 1) * (rank > 4 ? n4 : 1) * (rank > 5 ? n5 : 1) * sizeof(value_type) + 8;
+    return (rank > 0 ? n0 : 1) * (rank > 1 ? n1 : 1) * (rank > 2 ? n2 : 1) * (rank > 3 ? n3 : 1) * (rank > 4 ? n4 : 1) * (rank > 5 ? n5 : 1) * sizeof(value_type) + scratch_value_alignment;
   }
 
   KB200_INLINE_FUNCTION View(const View& o) : m_data(o.m_data), m_rec(o.m_rec) { copy_ext(o); retain(); }
@@ -226,6 +265,9 @@ class View {
   KB200_INLINE_FUNCTION void set_extents(size_t n0, size_t n1, size_t n2, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) {
     m_ext[0] = rank > 0 ? n0 : 1; m_ext[1] = rank > 1 ? n1 : 1; m_ext[2] = rank > 2 ? n2 : 1;
     m_ext[3] = rank > 3 ? n3 : 1; m_ext[4] = rank > 4 ? n4 : 1; m_ext[5] = rank > 5 ? n5 : 1;
+    // static extents occupy the dimensions after the dynamic ones
+    constexpr int dyn = Impl::data_type_dynamic_rank<DataType>::value;
+    for (int r = dyn; r < rank; ++r) m_ext[r] = Impl::data_type_static<DataType>::get(r - dyn);
   }
   KB200_INLINE_FUNCTION void copy_ext(const View& o) { for (int r = 0; r < 6; ++r) m_ext[r] = o.m_ext[r]; }
   KB200_INLINE_FUNCTION void retain() {

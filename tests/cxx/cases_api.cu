@@ -465,6 +465,48 @@ int kb200_case_team_collectives(int league, int team_size, int vec, int n_inner,
   });
 }
 
+// multi-level scratch carving (TestTeam.hpp:920-1036 pattern): three team-level and three thread-level Views per level, carved by
+// successive team_scratch(l) / thread_scratch(l) calls; out[0..3] = mismatches in team L0, thread L0, team L1, thread L1
+int kb200_case_multilevel_scratch(int league, int team_size, int vec, i64* out) {
+  return guarded([&] {
+    using TP = TeamPolicy<>;
+    using UV = View<double*, B200, MemoryTraits<Unmanaged>>;
+    View<i64*> err("err", 4);
+    TP pol(league, team_size, vec);
+    pol.set_scratch_size(0, PerTeam(3 * UV::shmem_size(128)), PerThread(3 * UV::shmem_size(16)))
+       .set_scratch_size(1, PerTeam(3 * UV::shmem_size(12800)), PerThread(3 * UV::shmem_size(1600)));
+    parallel_for("mls", pol, KB200_LAMBDA(const TP::member_type& team) {
+      UV at1(team.team_scratch(0), 128), ah1(team.thread_scratch(0), 16), at2(team.team_scratch(0), 128), ah2(team.thread_scratch(0), 16);
+      UV bt1(team.team_scratch(1), 12800), bh1(team.thread_scratch(1), 1600), bt2(team.team_scratch(1), 12800), bh2(team.thread_scratch(1), 1600);
+      UV at3(team.team_scratch(0), 128), ah3(team.thread_scratch(0), 16), bt3(team.team_scratch(1), 12800), bh3(team.thread_scratch(1), 1600);
+      const int lr = team.league_rank(), tr = team.team_rank();
+      parallel_for(TeamThreadRange(team, int(0), unsigned(128)), [&](const int& i) { at1(i) = 1e6 + i + lr * 1e5; at2(i) = 2e6 + i + lr * 1e5; at3(i) = 3e6 + i + lr * 1e5; });
+      team.team_barrier();
+      parallel_for(ThreadVectorRange(team, int(0), unsigned(16)), [&](const int& i) { ah1(i) = 1e6 + 1e5 * tr + 16 - i + lr * 1e5; ah2(i) = 2e6 + 1e5 * tr + 16 - i + lr * 1e5; ah3(i) = 3e6 + 1e5 * tr + 16 - i + lr * 1e5; });
+      parallel_for(TeamThreadRange(team, int(0), unsigned(12800)), [&](const int& i) { bt1(i) = 1e6 + i + lr * 1e5; bt2(i) = 2e6 + i + lr * 1e5; bt3(i) = 3e6 + i + lr * 1e5; });
+      team.team_barrier();
+      parallel_for(ThreadVectorRange(team, 1600), [&](const int& i) { bh1(i) = 1e6 + 1e5 * tr + 16 - i + lr * 1e5; bh2(i) = 2e6 + 1e5 * tr + 16 - i + lr * 1e5; bh3(i) = 3e6 + 1e5 * tr + 16 - i + lr * 1e5; });
+      team.team_barrier();
+      parallel_for(TeamThreadRange(team, 0, 128), [&](const int& i) {
+        if (at1(i) != 1e6 + i + lr * 1e5 || at2(i) != 2e6 + i + lr * 1e5 || at3(i) != 3e6 + i + lr * 1e5) atomic_add(&err(0), (i64)1); });
+      team.team_barrier();
+      parallel_for(ThreadVectorRange(team, 16), [&](const int& i) {
+        if (ah1(i) != 1e6 + 1e5 * tr + 16 - i + lr * 1e5 || ah2(i) != 2e6 + 1e5 * tr + 16 - i + lr * 1e5 || ah3(i) != 3e6 + 1e5 * tr + 16 - i + lr * 1e5) atomic_add(&err(1), (i64)1); });
+      parallel_for(TeamThreadRange(team, 0, 12800), [&](const int& i) {
+        if (bt1(i) != 1e6 + i + lr * 1e5 || bt2(i) != 2e6 + i + lr * 1e5 || bt3(i) != 3e6 + i + lr * 1e5) atomic_add(&err(2), (i64)1); });
+      team.team_barrier();
+      parallel_for(ThreadVectorRange(team, 1600), [&](const int& i) {
+        if (bh1(i) != 1e6 + 1e5 * tr + 16 - i + lr * 1e5 || bh2(i) != 2e6 + 1e5 * tr + 16 - i + lr * 1e5 || bh3(i) != 3e6 + 1e5 * tr + 16 - i + lr * 1e5) atomic_add(&err(3), (i64)1); });
+      if (at1.data() == nullptr || at3.data() == nullptr || ah3.data() == nullptr || bt3.data() == nullptr || bh3.data() == nullptr) atomic_add(&err(0), (i64)1000000);
+    });
+    fence();
+    View<i64*, HostSpace> h("h", 4);
+    deep_copy(h, err);
+    for (int k = 0; k < 4; ++k) out[k] = h(k);
+    return 0;
+  });
+}
+
 // ------------------------------------------------------------------ atomics (TestAtomics.hpp:456-598 style loops)
 int kb200_case_atomics(i64 n, double* out) {
   return guarded([&] {

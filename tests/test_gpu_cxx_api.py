@@ -218,6 +218,13 @@ def test_team_collectives_scratch_and_nested_scans(cases, league, team, vec, n_i
     assert out[10] == 0                                # nested TeamThreadRange scan through level-0 scratch
 
 
+def test_multilevel_scratch_carving(cases):
+    """Successive team_scratch(l)/thread_scratch(l) calls carve successive, non-overlapping pieces at both levels (TestTeam.hpp:920-1036)."""
+    out = np.zeros(4, dtype=np.int64)
+    ok(cases, cases.kb200_case_multilevel_scratch(10, 8, 16, P(out)))
+    assert list(out) == [0, 0, 0, 0]
+
+
 def test_atomics_all_ops(cases):
     n = 100003
     out = np.zeros(32)
