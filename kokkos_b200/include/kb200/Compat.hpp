@@ -6,6 +6,7 @@
 #define KB200_COMPAT_HPP
 
 #include "View.hpp"
+#include "Atomic.hpp"
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <typeinfo>
@@ -170,6 +171,39 @@ template <class T> struct is_memory_space
 template <class T> inline constexpr bool is_memory_space_v = is_memory_space<T>::value;
 
 }  // namespace kb200
+
+// The two wrap-around counters of desul that Kokkos does not re-export (tpls/desul/include/desul/atomics/Fetch_Op_Generic.hpp;
+// used directly by core/unit_test/TestAtomicOperations.hpp:336-380): old value returned, new value = (old >= wrap) ? 0 : old + 1
+// resp. (old == 0 || old > wrap) ? wrap : old - 1.  Memory order / scope tags are accepted (relaxed, device scope is what the
+// Kokkos wrappers always request: core/src/Kokkos_Atomics_Desul_Wrapper.hpp:72-148).
+namespace desul {
+struct MemoryOrderRelaxed {};
+struct MemoryOrderSeqCst {};
+struct MemoryOrderAcqRel {};
+struct MemoryScopeDevice {};
+struct MemoryScopeCore {};
+struct MemoryScopeSystem {};
+template <class T, class Order, class Scope>
+KB200_FORCEINLINE_FUNCTION T atomic_fetch_inc_mod(T* p, T wrap, Order, Scope) {
+  T old = kb200::atomic_load(p);
+  while (true) {
+    const T nw = old >= wrap ? T(0) : (T)(old + T(1));
+    const T seen = kb200::atomic_compare_exchange(p, old, nw);
+    if (seen == old) return old;
+    old = seen;
+  }
+}
+template <class T, class Order, class Scope>
+KB200_FORCEINLINE_FUNCTION T atomic_fetch_dec_mod(T* p, T wrap, Order, Scope) {
+  T old = kb200::atomic_load(p);
+  while (true) {
+    const T nw = (old == T(0) || old > wrap) ? wrap : (T)(old - T(1));
+    const T seen = kb200::atomic_compare_exchange(p, old, nw);
+    if (seen == old) return old;
+    old = seen;
+  }
+}
+}  // namespace desul
 
 // warning-control macros the reference's sources use around tests (core/src/Kokkos_Macros.hpp)
 #define KOKKOS_IMPL_DISABLE_UNREACHABLE_WARNINGS_PUSH()
