@@ -117,6 +117,38 @@ int kb200_perf_stream(int op, i64 n, int warm, int reps, double* out_ms) {
   });
 }
 
+// C2 tuning variants of the generic parallel_for launch shape (BLOCK x UNROLL, plain or persistent grid), copy lambda
+int kb200_perf_for_variant(int variant, i64 n, int warm, int reps, double* out_ms) {
+  return guarded([&] {
+    View<double*> a(view_alloc(WithoutInitializing, "a"), (size_t)n), c(view_alloc(WithoutInitializing, "c"), (size_t)n);
+    parallel_for("init", n, KB200_LAMBDA(const i64 i) { a(i) = 1.0; c(i) = 0.5; });
+    fence();
+    auto f = KB200_LAMBDA(const i64 i) { c(i) = a(i); };
+    using F = decltype(f);
+    using Body = Impl::FunctorForBody<F, void, i64>;
+    Body body{f, 0};
+    b200_instance* inst = B200().impl_instance();
+    auto run = [&](auto launcher, int bps) {
+      using L = decltype(launcher);
+      time_call([&] { Impl::throw_on_error(L::run(inst, body, n, bps)); }, warm, reps, out_ms);
+    };
+    switch (variant) {
+      case 0: run(Impl::RangeForLaunch<Body, 256, 4>{}, 0); break;
+      case 1: run(Impl::RangeForLaunch<Body, 256, 1>{}, 0); break;
+      case 2: run(Impl::RangeForLaunch<Body, 256, 2>{}, 0); break;
+      case 3: run(Impl::RangeForLaunch<Body, 256, 8>{}, 0); break;
+      case 4: run(Impl::RangeForLaunch<Body, 128, 1>{}, 0); break;
+      case 5: run(Impl::RangeForLaunch<Body, 512, 1>{}, 0); break;
+      case 6: run(Impl::RangeForLaunch<Body, 1024, 1>{}, 0); break;
+      case 7: run(Impl::RangeForLaunch<Body, 256, 4>{}, 8); break;   // persistent
+      case 8: run(Impl::RangeForLaunch<Body, 256, 1>{}, 8); break;
+      case 9: run(Impl::RangeForLaunch<Body, 512, 2>{}, 0); break;
+      default: return -1;
+    }
+    return 0;
+  });
+}
+
 // C3 tuning variants of the generic scan's tile shape (BLOCK x ITEMS), same lambda; variant 0 = the public parallel_scan
 int kb200_perf_scan_variant(int variant, i64 n, int warm, int reps, double* out_ms, i64* total) {
   return guarded([&] {
