@@ -251,6 +251,9 @@ int array_reduce_launch(const MDRangePolicy<P...>& policy, const F& f, int count
     k<<<grid, sh.block, 0, rt.stream()>>>(f, sh.p, count, partials, ticket, dst);
   });
 }
+template <class T, class Tag, class F, class... P, int CAP>
+int array_reduce_launch(const TeamPolicy<P...>& pol, const F& f, int count, T* rh, T* rd, std::integral_constant<int, CAP>);  // Team.hpp
+
 template <class Policy, class F, class R>
 void array_reduce_entry(const Policy& policy, const F& f, R&& result) {
   using T = std::remove_extent_t<typename F::value_type>;
@@ -349,7 +352,7 @@ template <class R, class = void>
 struct combined_slot {  // plain scalar reference: summed
   using value_type = std::remove_reference_t<R>;
   using reducer_type = DefaultSumReducer<value_type>;
-  static reducer_type reducer(R&) { return {}; }
+  KB200_INLINE_FUNCTION static reducer_type reducer(R&) { return {}; }
   static void store(const B200&, R& dst, const value_type& v) { dst = v; }
 };
 template <class R>
@@ -357,7 +360,7 @@ struct combined_slot<R, std::enable_if_t<is_view_v<R>>> {  // rank-0 View: summe
   using VT = std::decay_t<R>;
   using value_type = typename VT::non_const_value_type;
   using reducer_type = DefaultSumReducer<value_type>;
-  static reducer_type reducer(const VT&) { return {}; }
+  KB200_INLINE_FUNCTION static reducer_type reducer(const VT&) { return {}; }
   static void store(const B200& space, const VT& dst, const value_type& v) {
     copy_bytes<typename VT::memory_space, HostSpace>(space, (void*)dst.data(), &v, sizeof(value_type));
   }
@@ -367,7 +370,7 @@ struct combined_slot<R, std::enable_if_t<is_reducer_v<std::decay_t<R>>>> {  // r
   using RD = std::decay_t<R>;
   using value_type = typename RD::value_type;
   using reducer_type = ReducerAdapter<RD>;
-  static reducer_type reducer(const RD& r) { return reducer_type{r}; }
+  KB200_INLINE_FUNCTION static reducer_type reducer(const RD& r) { return reducer_type{r}; }
   static void store(const B200& space, const RD& r, const value_type& v) {
     if (r.references_scalar()) r.reference() = v;
     else throw_on_error(b200_memcpy_h2d_async(space.impl_instance(), (void*)r.data(), &v, sizeof(value_type)));
@@ -396,9 +399,9 @@ struct CombinedReducer {
   KB200_FORCEINLINE_FUNCTION void join(CV& d, const CV& s) const { rs.join(d, s); }
   KB200_FORCEINLINE_FUNCTION void final(CV& v) const { rs.final(v); }
 };
-inline CombinedReducers<> make_combined_reducers() { return {}; }
+KB200_INLINE_FUNCTION CombinedReducers<> make_combined_reducers() { return {}; }
 template <class R0, class... Rs>
-CombinedReducers<R0, Rs...> make_combined_reducers(const R0& r0, const Rs&... rs) { return CombinedReducers<R0, Rs...>{r0, make_combined_reducers(rs...)}; }
+KB200_INLINE_FUNCTION CombinedReducers<R0, Rs...> make_combined_reducers(const R0& r0, const Rs&... rs) { return CombinedReducers<R0, Rs...>{r0, make_combined_reducers(rs...)}; }
 
 // calls f(leading args..., v0, v1, ...): leading args are the index / indices / team handle (and the work tag)
 template <class F, class CV, int N>

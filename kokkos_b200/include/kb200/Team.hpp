@@ -274,9 +274,25 @@ template <class T> struct NestedSum {
   KB200_TEAM_FUNCTION void join(T& d, const T& s) const { d += s; }
   KB200_TEAM_FUNCTION void final(T&) const {}
 };
+// a nested functor that brings its own init/join acts as its reducer (TestTeam.hpp:1844-1870); final() is not applied at this
+// level, exactly like the reducer-object form
+template <class L, class T> struct NestedFunctorReducer {
+  using value_type = T;
+  const L& f;
+  KB200_TEAM_FUNCTION void init(T& v) const { if constexpr (has_init<L, T>::value) f.init(v); else v = T(); }
+  KB200_TEAM_FUNCTION void join(T& d, const T& s) const { if constexpr (has_join<L, T>::value) f.join(d, s); else d += s; }
+  KB200_TEAM_FUNCTION void final(T&) const {}
+};
+template <class L, class T>
+using nested_reducer_t = std::conditional_t<has_join<L, T>::value || has_init<L, T>::value, NestedFunctorReducer<L, T>, NestedSum<T>>;
+template <class L, class T>
+KB200_TEAM_FUNCTION nested_reducer_t<L, T> make_nested_reducer(const L& f) {
+  if constexpr (has_join<L, T>::value || has_init<L, T>::value) return NestedFunctorReducer<L, T>{f};
+  else return NestedSum<T>{};
+}
 }  // namespace Impl
 
-// ---- nested parallel_reduce: result is a scalar (sum) or a reducer
+// ---- nested parallel_reduce: result is a scalar (sum, or the functor's own init/join) or a reducer
 template <class I, class L, class R>
 KB200_TEAM_FUNCTION void parallel_reduce(const Impl::ThreadVectorRangeStruct<I>& r, const L& f, R&& result) {
   using RD = std::decay_t<R>;
@@ -287,9 +303,11 @@ KB200_TEAM_FUNCTION void parallel_reduce(const Impl::ThreadVectorRangeStruct<I>&
     Impl::vector_reduce(Impl::ReducerAdapter<RD>{result}, v);
     result.reference() = v;
   } else {
-    RD v = RD();
+    const auto red = Impl::make_nested_reducer<L, RD>(f);
+    RD v;
+    red.init(v);
     for (I i = r.begin + (I)Impl::tm::tx(); i < r.end; i += (I)Impl::tm::nx()) f(i, v);
-    Impl::vector_reduce(Impl::NestedSum<RD>{}, v);
+    Impl::vector_reduce(red, v);
     result = v;
   }
 }
@@ -303,9 +321,11 @@ KB200_TEAM_FUNCTION void parallel_reduce(const Impl::TeamThreadRangeStruct<I>& r
     r.member.team_reduce(Impl::ReducerAdapter<RD>{result}, v);
     result.reference() = v;
   } else {
-    RD v = RD();
+    const auto red = Impl::make_nested_reducer<L, RD>(f);
+    RD v;
+    red.init(v);
     for (I i = r.begin + (I)Impl::tm::ty(); i < r.end; i += (I)Impl::tm::ny()) f(i, v);
-    r.member.team_reduce(Impl::NestedSum<RD>{}, v);
+    r.member.team_reduce(red, v);
     result = v;
   }
 }
@@ -321,12 +341,53 @@ KB200_TEAM_FUNCTION void parallel_reduce(const Impl::TeamVectorRangeStruct<I>& r
     r.member.team_reduce(Impl::ReducerAdapter<RD>{result}, v);
     result.reference() = v;
   } else {
-    RD v = RD();
+    const auto red = Impl::make_nested_reducer<L, RD>(f);
+    RD v;
+    red.init(v);
     for (I i = start; i < r.end; i += step) f(i, v);
-    Impl::vector_reduce(Impl::NestedSum<RD>{}, v);
-    r.member.team_reduce(Impl::NestedSum<RD>{}, v);
+    Impl::vector_reduce(red, v);
+    r.member.team_reduce(red, v);
     result = v;
   }
+}
+
+// ---- nested parallel_reduce with several results: parallel_reduce(nested_range, f(i, v0&, v1&, ...), r0, r1, ...) where each
+//      r_k is a scalar (sum) or a reducer (core/unit_test/TestTeamCombinedReducers.hpp): the values travel as one CombinedValue
+//      through the single-result nested reduction above
+namespace Impl {
+template <class CV, class... Rs>
+struct NestedCombinedReducer {
+  using reducer = NestedCombinedReducer;
+  using value_type = CV;
+  CombinedReducers<typename combined_slot<Rs>::reducer_type...> rs;
+  CV* out;
+  KB200_TEAM_FUNCTION void init(CV& v) const { rs.init(v); }
+  KB200_TEAM_FUNCTION void join(CV& d, const CV& s) const { rs.join(d, s); }
+  KB200_TEAM_FUNCTION CV& reference() const { return *out; }
+};
+template <class R, class V>
+KB200_TEAM_FUNCTION void nested_store(R& r, const V& v) {
+  if constexpr (is_reducer_v<std::decay_t<R>>) r.reference() = v; else r = v;
+}
+template <class CV, class... Rs, size_t... Is>
+KB200_TEAM_FUNCTION void nested_store_all(const CV& v, std::index_sequence<Is...>, Rs&... rs) {
+  (nested_store(rs, combined_get<(int)Is>(v)), ...);
+}
+template <class T> struct is_nested_range : std::false_type {};
+template <class I> struct is_nested_range<ThreadVectorRangeStruct<I>> : std::true_type {};
+template <class I> struct is_nested_range<TeamThreadRangeStruct<I>> : std::true_type {};
+template <class I> struct is_nested_range<TeamVectorRangeStruct<I>> : std::true_type {};
+}  // namespace Impl
+template <class Range, class L, class R0, class R1, class... Rs, std::enable_if_t<Impl::is_nested_range<Range>::value, int> = 0>
+KB200_TEAM_FUNCTION void parallel_reduce(const Range& r, const L& f, R0&& r0, R1&& r1, Rs&&... rs) {
+  using CV = Impl::CombinedValue<typename Impl::combined_slot<R0>::value_type, typename Impl::combined_slot<R1>::value_type,
+                                 typename Impl::combined_slot<Rs>::value_type...>;
+  constexpr int N = 2 + (int)sizeof...(Rs);
+  CV result;
+  Impl::NestedCombinedReducer<CV, R0, R1, Rs...> red{
+      Impl::make_combined_reducers(Impl::combined_slot<R0>::reducer(r0), Impl::combined_slot<R1>::reducer(r1), Impl::combined_slot<Rs>::reducer(rs)...), &result};
+  parallel_reduce(r, [&](const decltype(r.begin) i, CV& v) { Impl::CombinedFunctor<const L&, CV, N>{f}(i, v); }, red);
+  Impl::nested_store_all(result, std::make_index_sequence<N>{}, r0, r1, rs...);
 }
 
 // ---- nested parallel_scan, f(i, partial, final); ThreadVectorRange and TeamThreadRange
@@ -539,6 +600,8 @@ template <class F>
 struct team_reduce_value_of<F, std::void_t<typename F::value_type>> { using type = typename F::value_type; };
 template <class F, class = void> struct team_reduce_value_known : std::false_type {};
 template <class F> struct team_reduce_value_known<F, std::void_t<typename team_reduce_value_of<F>::type>> : std::true_type {};
+template <class F, bool = team_reduce_value_known<F>::value> struct team_reduce_scalar_value_known : std::false_type {};
+template <class F> struct team_reduce_scalar_value_known<F, true> : std::integral_constant<bool, !std::is_array<typename team_reduce_value_of<F>::type>::value> {};
 
 template <class Policy, class F, class PatternTag>
 int team_size_limit(const Policy& pol, const F& f, const PatternTag&) {
@@ -548,10 +611,11 @@ int team_size_limit(const Policy& pol, const F& f, const PatternTag&) {
   size_t value_bytes = 16;
   bool halve = false;
   if constexpr (std::is_same<PatternTag, ParallelReduceTag>::value) {
-    if constexpr (team_reduce_value_known<F>::value) {
+    if constexpr (team_reduce_scalar_value_known<F>::value) {
       using V = typename team_reduce_value_of<F>::type;
+      using Red = std::conditional_t<brings_reduction_members<F, V, Tag>::value, FunctorReducer<F, V, Tag>, DefaultSumReducer<V>>;
       value_bytes = sizeof(V);
-      throw_on_error(b200_report_error((int)cudaFuncGetAttributes(&attr, team_reduce_kernel<F, Tag, DefaultSumReducer<V>>), "kb200::team_size_max"));
+      throw_on_error(b200_report_error((int)cudaFuncGetAttributes(&attr, team_reduce_kernel<F, Tag, Red>), "kb200::team_size_max"));
     } else {  // value type only known with the result argument: bound it by the for-kernel of the same functor, halved
       attr.maxThreadsPerBlock = 1024;
       halve = true;
@@ -590,6 +654,42 @@ void parallel_for(const std::string& /*label*/, const TeamPolicy<P...>& pol, con
 }
 template <class... P, class F>
 void parallel_for(const TeamPolicy<P...>& pol, const F& f) { parallel_for(std::string(), pol, f); }
+
+namespace Impl {
+// TeamPolicy reduction with a runtime-length array value (value_type = T[], value_count): per-thread accumulator arrays as in
+// ArrayReduceKernel.hpp; one contribution per team thread (vector lanes other than 0 are reset to the identity)
+template <class F, class Tag, class T, int CAP>
+__global__ void array_team_reduce_kernel(const __grid_constant__ F f, const TeamLaunchParams p, const int count, T* partials, unsigned* ticket,
+                                         T* result) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ T red_smem[32 * CAP];
+  T acc[CAP];
+  ArrayOps<F, T>::init(f, acc, count);
+  for (int lr = blockIdx.x; lr < p.league_size; lr += gridDim.x) {
+    B200TeamMember m(smem, smem + kTeamCollectiveBytes, p.l0_team, p.l0_thread, p.l1_arena + (size_t)blockIdx.x * p.l1_per_team,
+                     p.l1_team, p.l1_thread, lr, p.league_size);
+    if constexpr (std::is_void<Tag>::value) f(m, acc); else f(Tag{}, m, acc);
+    if (lr + (int)gridDim.x < p.league_size) __syncthreads();
+  }
+  if (threadIdx.x != 0) ArrayOps<F, T>::init(f, acc, count);
+  __syncthreads();
+  array_block_reduce<F, T, CAP>(f, acc, count, red_smem);
+  __syncthreads();
+  array_grid_reduce_and_store<F, T, CAP>(f, acc, count, partials, ticket, result, red_smem);
+}
+template <class T, class Tag, class F, class... P, int CAP>
+int array_reduce_launch(const TeamPolicy<P...>& pol, const F& f, int count, T* rh, T* rd, std::integral_constant<int, CAP>) {
+  auto k = array_team_reduce_kernel<F, Tag, T, CAP>;
+  TeamShape<TeamPolicy<P...>> sh;
+  int rc = sh.setup(pol, (const void*)k, 16, f);
+  if (rc) return rc;
+  b200_instance* inst = pol.space().impl_instance();
+  HostRuntime rt(inst);
+  return array_reduce_run<T>(inst, count, sh.grid, rh, rd, [&](T* partials, unsigned* ticket, T* dst) {
+    k<<<sh.grid, dim3(sh.vec, sh.team, 1), sh.smem, rt.stream()>>>(f, sh.p, count, partials, ticket, dst);
+  });
+}
+}  // namespace Impl
 
 namespace Impl {
 template <class... P, class F, class Red>
