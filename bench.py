@@ -300,7 +300,7 @@ def main():
             assert torch.equal(hy[: 1 << 20].to(dev), torch.cumsum(xi[: 1 << 20], 0) - xi[: 1 << 20])
             e2e = {"value": bytes_per_step / (float(w.item()) / e2e_steps) / 1e9, "unit": "GB/s",
                    "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n + 16, "steps": e2e_steps,
-                   "api": "b200_reduce_sum_f64_host + b200_scan_excl_i64_host (pinned host buffers, 256 MiB chunks, double-buffered)",
+                   "api": "b200_reduce_sum_f64_host + b200_scan_excl_i64_host (pinned host buffers, 64 MiB chunks, double-buffered)",
                    "note": "per-GPU shards are independent on this leg (no cross-GPU seed): PCIe-bound"}
             del hx, hi, hy
         except Exception as ex:  # e.g. not enough pinnable host memory

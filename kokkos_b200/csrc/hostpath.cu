@@ -17,7 +17,7 @@
 
 namespace {
 
-constexpr int64_t kChunkBytes = 256ll << 20;  // per staging buffer
+constexpr int64_t kChunkBytes = 64ll << 20;  // per staging buffer: small enough that the un-overlapped first H2D / last D2H are ~1 ms
 constexpr int kDepth = 2;
 
 struct HostPipe {
