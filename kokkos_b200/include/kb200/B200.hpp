@@ -15,7 +15,9 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <array>
 #include <memory>
+#include <utility>
 #include <ostream>
 #include <stdexcept>
 #include <string>
@@ -162,11 +164,16 @@ struct ScopeGuard {
 namespace Experimental {
 // Kokkos::Experimental::partition_space: n independent instances (own streams) on the same device
 // (core/src/Cuda/Kokkos_Cuda_Instance.hpp:368-385)
-template <class... W>
-std::vector<B200> partition_space(const B200& base, W... /*weights*/) {
-  std::vector<B200> out;
-  for (size_t k = 0; k < sizeof...(W); ++k) out.push_back(B200::on_device(base.cuda_device()));
-  return out;
+namespace detail {
+template <size_t... Is>
+std::array<B200, sizeof...(Is)> make_instances(int device, std::index_sequence<Is...>) {
+  return std::array<B200, sizeof...(Is)>{((void)Is, B200::on_device(device))...};
+}
+}  // namespace detail
+// weights given as arguments: a std::array (usable with structured bindings); as a vector: a std::vector
+template <class... W, class = std::enable_if_t<(std::is_arithmetic<W>::value && ...)>>
+std::array<B200, sizeof...(W)> partition_space(const B200& base, W... /*weights*/) {
+  return detail::make_instances(base.cuda_device(), std::make_index_sequence<sizeof...(W)>{});
 }
 inline std::vector<B200> partition_space(const B200& base, const std::vector<int>& weights) {
   std::vector<B200> out;

@@ -258,6 +258,8 @@ class TeamPolicy {
     const int ts = team_size > 0 ? team_size : (m_team > 0 ? m_team : 1);
     return m_team_scratch[level] + m_thread_scratch[level] * (size_t)ts;
   }
+  int chunk_size() const { return m_chunk; }   // accepted and ignored by the launch (league members are strided over a persistent grid)
+  TeamPolicy& set_chunk_size(int c) { m_chunk = c; return *this; }
   size_t team_scratch_size(int level) const { return m_team_scratch[level]; }
   size_t thread_scratch_size(int level) const { return m_thread_scratch[level]; }
   TeamPolicy& set_scratch_size(int level, PerTeamValue t) { chk_level(level); m_team_scratch[level] = t.value; return *this; }
@@ -288,6 +290,7 @@ class TeamPolicy {
   }
   B200 m_space;
   int m_league = 0, m_team = -1, m_vec = 1;
+  int m_chunk = 32;  // Cuda/Kokkos_Cuda_Parallel_Team.hpp: default chunk = warp size
   size_t m_team_scratch[2] = {0, 0}, m_thread_scratch[2] = {0, 0};
 };
 
