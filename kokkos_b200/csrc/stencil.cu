@@ -216,6 +216,13 @@ KB200_DEVICE_FUNCTION void stencil_refresh_thresholds(const V& acc, double& tmin
   tmin = a; tmax = b;
 }
 
+// probe modes exist only in the sweep build (tools/stencil_probe.py --sweep --dbg); the shipped kernel has no such branches
+#ifdef B200_SWEEP
+#define KB200_STENCIL_DBG(P, X) ((P).dbg == (X))
+#else
+#define KB200_STENCIL_DBG(P, X) false
+#endif
+
 struct StencilTmaParams {
   const double* u;
   double* vout;
@@ -253,7 +260,7 @@ struct StencilProducer {
   KB200_DEVICE_FUNCTION void issue(const StencilTmaParams& p, int n0, double* stages, int stage_elems, unsigned long long* full,
                                    unsigned long long* empty) {
     if (tile >= p.tiles_j * p.tiles_k) return;
-    if (p.dbg == 2) { tile = p.tiles_j * p.tiles_k; return; }  // probe: no data movement
+    if (KB200_STENCIL_DBG(p, 2)) { tile = p.tiles_j * p.tiles_k; return; }  // probe: no data movement
     const unsigned s = x % NS, use = x / NS;
     if (use > 0) ptx::mbar_wait(&empty[s], (use & 1u) ^ 1u);
     ptx::mbar_expect_tx(&full[s], bytes);
@@ -288,7 +295,7 @@ __global__ void __launch_bounds__(CT + (PW ? 32 : 0), 1) stencil7_tma_kernel(con
     double* q = stages + (size_t)tid * stage_elems + pad;
     q[0] = qnan; q[1] = qnan; q[n0] = qnan; q[n0 + 1] = qnan;
   }
-  if (p.dbg == 2)  // probe: arithmetic on resident pseudo-random data
+  if (KB200_STENCIL_DBG(p, 2))  // probe: arithmetic on resident pseudo-random data
     for (int q = tid; q < NS * stage_elems; q += blockDim.x) stages[q] = (double)((q * 2654435761u) >> 8) * (1.0 / 16777216.0);
   __syncthreads();
   const StencilRed red;
@@ -343,7 +350,7 @@ __global__ void __launch_bounds__(CT + (PW ? 32 : 0), 1) stencil7_tma_kernel(con
       double2 ra[UPT][2], rb[UPT][2], rc[UPT][2];  // three rotating plane buffers: no register moves between steps
       {  // k0-1 and k0 centres -> registers
         const unsigned s0 = pos % NS, s1 = (pos + 1) % NS;
-        if (p.dbg != 2) ptx::mbar_wait(&full[s0], (pos / NS) & 1u);
+        if (!KB200_STENCIL_DBG(p, 2)) ptx::mbar_wait(&full[s0], (pos / NS) & 1u);
         const double* P = stages + (size_t)s0 * stage_elems;
 #pragma unroll
         for (int m = 0; m < UPT; ++m) {
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(CT + (PW ? 32 : 0), 1) stencil7_tma_kernel(con
           ra[m][1] = *reinterpret_cast<const double2*>(P + un[m].off + n0);
         }
         KB200_STENCIL_RELEASE(s0)
-        if (p.dbg != 2) ptx::mbar_wait(&full[s1], ((pos + 1) / NS) & 1u);
+        if (!KB200_STENCIL_DBG(p, 2)) ptx::mbar_wait(&full[s1], ((pos + 1) / NS) & 1u);
         const double* Q = stages + (size_t)s1 * stage_elems;
 #pragma unroll
         for (int m = 0; m < UPT; ++m) {
@@ -364,12 +371,12 @@ __global__ void __launch_bounds__(CT + (PW ? 32 : 0), 1) stencil7_tma_kernel(con
       {                                                                                                                 \
         const int kk = k0 - 1 + t;                                                                                      \
         const unsigned scur = (pos + t) % NS, snext = (pos + t + 1) % NS;                                               \
-        if (p.dbg != 2) ptx::mbar_wait(&full[snext], ((pos + t + 1) / NS) & 1u);                                        \
+        if (!KB200_STENCIL_DBG(p, 2)) ptx::mbar_wait(&full[snext], ((pos + t + 1) / NS) & 1u);                          \
         const double* P = stages + (size_t)scur * stage_elems;                                                          \
         const double* N = stages + (size_t)snext * stage_elems;                                                         \
         double* vplane = STORE ? p.vout + (size_t)n0 * ((size_t)j0 + (size_t)n1 * kk) : nullptr;                        \
         bool hit = false;                                                                                               \
-        if (p.dbg == 1) {                                                                                               \
+        if (KB200_STENCIL_DBG(p, 1)) {                                                                                  \
         } else if (full_tile) {                                                                                         \
           _Pragma("unroll") for (int m = 0; m < UPT; ++m)                                                               \
             if ((actmask >> m) & 1u)                                                                                    \

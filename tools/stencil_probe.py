@@ -26,7 +26,7 @@ def main():
     vout = torch.empty(n, dtype=torch.float64, device="cuda")
     vu, vv = space.wrap(u.data_ptr(), n, np.float64), space.wrap(vout.data_ptr(), n, np.float64)
     ref = None
-    if "--dbg" in sys.argv:
+    if "--dbg" in sys.argv:  # needs --sweep: the probe branches are compiled into the sweep library only
         for dbg in (0, 1, 2):
             kb.tune_set("stencil.dbg", dbg)
             b, m = time_it(lambda: space.stencil7_minmaxloc(vu, n0, n1, n2, 0.5, 0.125), side, 10)
