@@ -36,6 +36,7 @@
 #define KOKKOS_IMPL_HOST_FUNCTION __host__
 #define KOKKOS_IMPL_DEVICE_FUNCTION __device__
 #define KOKKOS_ENABLE_CUDA_LAMBDA
+#define KOKKOS_COMPILER_NVCC (__CUDACC_VER_MAJOR__ * 100 + __CUDACC_VER_MINOR__ * 10)  // as core/src/Kokkos_Macros.hpp
 #define KOKKOS_IF_ON_DEVICE(CODE) NV_IF_TARGET(NV_IS_DEVICE, CODE)
 #define KOKKOS_IF_ON_HOST(CODE) NV_IF_TARGET(NV_IS_HOST, CODE)
 #endif

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <initializer_list>
 
 namespace kb200 {
 
@@ -77,10 +78,24 @@ KB200_FORCEINLINE_FUNCTION void memory_fence() {
 #endif
 }
 
-namespace numbers {  // core/src/Kokkos_MathematicalConstants.hpp
-inline constexpr double pi = 3.141592653589793238462643383279502884;
-inline constexpr double e = 2.718281828459045235360287471352662498;
-inline constexpr double sqrt2 = 1.414213562373095048801688724209698079;
+namespace numbers {  // core/src/Kokkos_MathematicalConstants.hpp:30-75 (the C++20 <numbers> set; floating-point types only)
+#define KB200_MATH_CONSTANT(NAME, VALUE)                                                                               \
+  template <class T> inline constexpr auto NAME##_v = std::enable_if_t<std::is_floating_point<T>::value, T>(VALUE##L); \
+  inline constexpr double NAME = NAME##_v<double>;
+KB200_MATH_CONSTANT(e, 2.718281828459045235360287471352662498)
+KB200_MATH_CONSTANT(log2e, 1.442695040888963407359924681001892137)
+KB200_MATH_CONSTANT(log10e, 0.434294481903251827651128918916605082)
+KB200_MATH_CONSTANT(pi, 3.141592653589793238462643383279502884)
+KB200_MATH_CONSTANT(inv_pi, 0.318309886183790671537767526745028724)
+KB200_MATH_CONSTANT(inv_sqrtpi, 0.564189583547756286948079451560772586)
+KB200_MATH_CONSTANT(ln2, 0.693147180559945309417232121458176568)
+KB200_MATH_CONSTANT(ln10, 2.302585092994045684017991454684364208)
+KB200_MATH_CONSTANT(sqrt2, 1.414213562373095048801688724209698079)
+KB200_MATH_CONSTANT(sqrt3, 1.732050807568877293527446341505872367)
+KB200_MATH_CONSTANT(inv_sqrt3, 0.577350269189625764509148780501957456)
+KB200_MATH_CONSTANT(egamma, 0.577215664901532860606512090082402431)
+KB200_MATH_CONSTANT(phi, 1.618033988749894848204586834365638118)
+#undef KB200_MATH_CONSTANT
 }  // namespace numbers
 
 // Kokkos::printf (core/src/Kokkos_Printf.hpp): callable from host and device code
@@ -90,6 +105,8 @@ KB200_FORCEINLINE_FUNCTION void printf(const char* fmt, Args... args) {
   else ::printf(fmt, args...);
 }
 
+struct InvalidType {};  // core/src/Kokkos_Core_fwd.hpp:56: "no argument" marker in variadic test helpers
+
 // Kokkos::pair (core/src/Kokkos_Pair.hpp): std::pair usable in device code
 template <class T1, class T2>
 struct pair {
@@ -97,7 +114,7 @@ struct pair {
   using second_type = T2;
   T1 first;
   T2 second;
-  KB200_DEFAULTED_FUNCTION constexpr pair() = default;
+  constexpr pair() = default;
   KB200_FORCEINLINE_FUNCTION constexpr pair(const T1& f, const T2& s) : first(f), second(s) {}
   template <class U, class V>
   KB200_FORCEINLINE_FUNCTION constexpr pair(const pair<U, V>& p) : first(p.first), second(p.second) {}
@@ -120,9 +137,50 @@ KB200_FORCEINLINE_FUNCTION constexpr pair<T1, T2> make_pair(T1 a, T2 b) { return
 // Kokkos-namespace mode: a translation unit that says `using namespace kb200;` before CUDA's math headers would otherwise see
 // two candidates for every unqualified sqrt()/fabs() call inside those headers.
 #ifdef KB200_AS_KOKKOS
+// min / max / minmax / clamp with the std:: tie rules (core/src/Kokkos_MinMax.hpp:30-200): min and max return the FIRST of
+// equivalent arguments, minmax returns {leftmost smallest, rightmost largest}; each with an optional comparator and over a braced list
 template <class T> KB200_FORCEINLINE_FUNCTION constexpr const T& min(const T& a, const T& b) { return b < a ? b : a; }
 template <class T> KB200_FORCEINLINE_FUNCTION constexpr const T& max(const T& a, const T& b) { return a < b ? b : a; }
+template <class T, class C> KB200_FORCEINLINE_FUNCTION constexpr const T& min(const T& a, const T& b, C comp) { return comp(b, a) ? b : a; }
+template <class T, class C> KB200_FORCEINLINE_FUNCTION constexpr const T& max(const T& a, const T& b, C comp) { return comp(a, b) ? b : a; }
+template <class T, class C>
+KB200_FORCEINLINE_FUNCTION constexpr T min(std::initializer_list<T> l, C comp) {
+  auto it = l.begin();
+  auto best = it;
+  for (++it; it != l.end(); ++it)
+    if (comp(*it, *best)) best = it;
+  return *best;
+}
+template <class T, class C>
+KB200_FORCEINLINE_FUNCTION constexpr T max(std::initializer_list<T> l, C comp) {
+  auto it = l.begin();
+  auto best = it;
+  for (++it; it != l.end(); ++it)
+    if (comp(*best, *it)) best = it;
+  return *best;
+}
+namespace Impl { struct less_than { template <class A, class B> KB200_FORCEINLINE_FUNCTION constexpr bool operator()(const A& a, const B& b) const { return a < b; } }; }
+template <class T> KB200_FORCEINLINE_FUNCTION constexpr T min(std::initializer_list<T> l) { return kb200::min(l, Impl::less_than{}); }
+template <class T> KB200_FORCEINLINE_FUNCTION constexpr T max(std::initializer_list<T> l) { return kb200::max(l, Impl::less_than{}); }
+template <class T, class C>
+KB200_FORCEINLINE_FUNCTION constexpr pair<const T&, const T&> minmax(const T& a, const T& b, C comp) {
+  using R = pair<const T&, const T&>;
+  return comp(b, a) ? R{b, a} : R{a, b};
+}
+template <class T> KB200_FORCEINLINE_FUNCTION constexpr pair<const T&, const T&> minmax(const T& a, const T& b) { return kb200::minmax(a, b, Impl::less_than{}); }
+template <class T, class C>
+KB200_FORCEINLINE_FUNCTION constexpr pair<T, T> minmax(std::initializer_list<T> l, C comp) {
+  auto it = l.begin();
+  auto lo = it, hi = it;
+  for (++it; it != l.end(); ++it) {
+    if (comp(*it, *lo)) lo = it;
+    else if (!comp(*it, *hi)) hi = it;
+  }
+  return pair<T, T>{*lo, *hi};
+}
+template <class T> KB200_FORCEINLINE_FUNCTION constexpr pair<T, T> minmax(std::initializer_list<T> l) { return kb200::minmax(l, Impl::less_than{}); }
 template <class T> KB200_FORCEINLINE_FUNCTION constexpr const T& clamp(const T& v, const T& lo, const T& hi) { return v < lo ? lo : (hi < v ? hi : v); }
+template <class T, class C> KB200_FORCEINLINE_FUNCTION constexpr const T& clamp(const T& v, const T& lo, const T& hi, C comp) { return comp(v, lo) ? lo : (comp(hi, v) ? hi : v); }
 #define KB200_MATH_1(NAME) \
   KB200_FORCEINLINE_FUNCTION double NAME(double x) { return ::NAME(x); } \
   KB200_FORCEINLINE_FUNCTION float NAME(float x) { return ::NAME##f(x); }

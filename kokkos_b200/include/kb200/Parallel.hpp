@@ -274,6 +274,16 @@ void array_reduce_entry(const Policy& policy, const F& f, R&& result) {
   throw_on_error(rc);
 }
 
+// where a reducer's result lives: the built-in reducers know (a scalar or a host View vs a device View); a user-written
+// reducer declares it through the memory space of its result_view_type (core/unit_test/TestReduceCombinatorical.hpp:27-56)
+template <class R, class = void> struct has_references_scalar : std::false_type {};
+template <class R> struct has_references_scalar<R, std::void_t<decltype(std::declval<const R&>().references_scalar())>> : std::true_type {};
+template <class R>
+bool reducer_result_on_host(const R& r) {
+  if constexpr (has_references_scalar<R>::value) return r.references_scalar();
+  else return !R::result_view_type::is_device;
+}
+
 template <class Policy, class F, class R>
 void reduce_entry(const Policy& policy, const F& f, R&& result) {
   using RD = std::decay_t<R>;
@@ -285,8 +295,8 @@ void reduce_entry(const Policy& policy, const F& f, R&& result) {
   if constexpr (is_reducer_v<RD>) {
     using V = typename RD::value_type;
     ReducerAdapter<RD> red{result};
-    ResultTarget<V> t = result.references_scalar() ? ResultTarget<V>{&result.reference(), nullptr}
-                                                   : ResultTarget<V>{nullptr, &result.reference()};
+    ResultTarget<V> t = reducer_result_on_host(result) ? ResultTarget<V>{&result.reference(), nullptr}
+                                                       : ResultTarget<V>{nullptr, &result.reference()};
     reduce_dispatch(policy, f, red, t);
   } else if constexpr (is_view_v<RD>) {
     using V = typename RD::non_const_value_type;
@@ -324,6 +334,35 @@ template <class F, class R>
 void parallel_reduce(size_t n, const F& f, R&& result) {
   Impl::reduce_entry(RangePolicy<>(0, (long long)n), f, static_cast<R&&>(result));
 }
+
+// ---- no result argument: the functor's final() consumes the value on the device (Kokkos_Parallel_Reduce.hpp:1555-1640;
+// core/unit_test/TestReduceCombinatorical.hpp:460-490).  The value type is F::value_type, else the last parameter of the
+// (non-template) call operator, as the reference's FunctorAnalysis deduces it.
+namespace Impl {
+template <class F>
+struct reduce_op_value {
+  template <class C, class R, class... A>
+  static std::remove_reference_t<std::tuple_element_t<sizeof...(A) - 1, std::tuple<A...>>> pick(R (C::*)(A...) const);
+  using type = decltype(pick(&F::operator()));
+};
+template <class F, class = void> struct reduce_value_type_of { using type = typename reduce_op_value<F>::type; };
+template <class F> struct reduce_value_type_of<F, std::void_t<typename F::value_type>> { using type = typename F::value_type; };
+template <class Policy, class F>
+void reduce_entry_no_result(const Policy& policy, const F& f) {
+  using V = typename reduce_value_type_of<F>::type;
+  static_assert(!std::is_array<V>::value, "parallel_reduce without a result argument: array value types need a result");
+  V unused{};  // handing it back costs one stream sync; final() has already run on the device by then
+  reduce_entry(policy, f, unused);
+}
+}  // namespace Impl
+template <class Policy, class F, class = std::enable_if_t<Impl::is_policy<Policy>::value>>
+void parallel_reduce(const std::string& /*label*/, const Policy& policy, const F& f) { Impl::reduce_entry_no_result(policy, f); }
+template <class Policy, class F, class = std::enable_if_t<Impl::is_policy<Policy>::value>>
+void parallel_reduce(const Policy& policy, const F& f) { Impl::reduce_entry_no_result(policy, f); }
+template <class F, class = std::enable_if_t<!Impl::is_policy<F>::value && std::is_class<F>::value>>
+void parallel_reduce(const std::string& /*label*/, size_t n, const F& f) { Impl::reduce_entry_no_result(RangePolicy<>(0, (long long)n), f); }
+template <class F, class = std::enable_if_t<std::is_class<F>::value>>
+void parallel_reduce(size_t n, const F& f) { Impl::reduce_entry_no_result(RangePolicy<>(0, (long long)n), f); }
 
 // =====================================================================================================
 // parallel_reduce with several results: parallel_reduce(label, policy, f, r0, r1, ...)   (row a22)
@@ -372,7 +411,7 @@ struct combined_slot<R, std::enable_if_t<is_reducer_v<std::decay_t<R>>>> {  // r
   using reducer_type = ReducerAdapter<RD>;
   KB200_INLINE_FUNCTION static reducer_type reducer(const RD& r) { return reducer_type{r}; }
   static void store(const B200& space, const RD& r, const value_type& v) {
-    if (r.references_scalar()) r.reference() = v;
+    if (reducer_result_on_host(r)) r.reference() = v;
     else throw_on_error(b200_memcpy_h2d_async(space.impl_instance(), (void*)r.data(), &v, sizeof(value_type)));
   }
 };

@@ -14,7 +14,9 @@
 #define KB200_POLICY_HPP
 
 #include "B200.hpp"
+#include "Array.hpp"
 #include <array>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -76,6 +78,45 @@ template <> struct index_of<void> { using type = long long; };
 template <class Policy, class F, class PatternTag>
 int team_size_limit(const Policy& pol, const F& f, const PatternTag&);
 
+// true when converting `bound` to Index does not preserve its value (sign change or narrowing):
+// core/src/Kokkos_ExecPolicy.hpp:258-290, core/src/KokkosExp_MDRangePolicy.hpp:60-95
+template <class Index, class T>
+constexpr bool index_conversion_unsafe(const T bound) {
+  if constexpr (std::is_convertible<Index, T>::value) {
+    bool unsafe = false;
+    if constexpr (std::is_arithmetic<T>::value && std::is_signed<T>::value != std::is_signed<Index>::value) {
+      if constexpr (std::is_signed<T>::value) unsafe = unsafe || bound < static_cast<T>(std::numeric_limits<Index>::min());
+      if constexpr (std::is_signed<Index>::value) unsafe = unsafe || bound > static_cast<T>(std::numeric_limits<Index>::max());
+    }
+    return unsafe || static_cast<T>(static_cast<Index>(bound)) != bound;
+  } else {
+    return false;
+  }
+}
+
+// defaults of the MDRange tiling on this device (the role of Impl::get_tile_size_properties, KokkosExp_MDRangePolicy.hpp:98-128
+// and Cuda/Kokkos_Cuda_MDRangePolicy.hpp:25-35): 32 threads along the contiguous dimension (one warp = one 256-byte row),
+// `default_tile_size` along every other dimension while the tile stays under max_total_tile_size
+struct TileSizeProperties {
+  int max_threads;
+  int default_largest_tile_size;
+  int default_tile_size;
+  int max_total_tile_size;
+  int max_threads_dimensions[3];
+};
+inline int md_default_tile_size() {
+  static const int v = [] {
+    const char* e = std::getenv("KB200_MD_DEFAULT_TILE");
+    const int t = e ? std::atoi(e) : 0;
+    return t > 0 && t <= 32 ? t : 4;
+  }();
+  return v;
+}
+template <class Space>
+TileSizeProperties get_tile_size_properties(const Space&) {
+  return TileSizeProperties{1024, 32, md_default_tile_size(), 1024, {1024, 1024, 64}};
+}
+
 [[noreturn]] inline void policy_abort(const char* msg) {
   std::fprintf(stderr, "%s", msg);
   if (msg[0] && msg[std::strlen(msg) - 1] != '\n') std::fprintf(stderr, "\n");
@@ -127,18 +168,10 @@ class RangePolicy {
   }
   template <class T>
   static index_type checked(const T bound) {
-    if constexpr (std::is_convertible<index_type, T>::value) {
-      bool unsafe = false;
-      if constexpr (std::is_arithmetic<T>::value && std::is_signed<T>::value != std::is_signed<index_type>::value) {
-        if constexpr (std::is_signed<T>::value) unsafe = unsafe || bound < static_cast<T>(std::numeric_limits<index_type>::min());
-        if constexpr (std::is_signed<index_type>::value) unsafe = unsafe || bound > static_cast<T>(std::numeric_limits<index_type>::max());
-      }
-      unsafe = unsafe || static_cast<T>(static_cast<index_type>(bound)) != bound;  // narrowing
-      if (unsafe) {
-        const std::string msg = std::string(KB200_NS_STR "::RangePolicy bound type error: an unsafe implicit conversion is performed on a bound (") +
-                                std::to_string(bound) + "), which may not preserve its original value.\n";
-        Impl::policy_abort(msg.c_str());
-      }
+    if (Impl::index_conversion_unsafe<index_type>(bound)) {
+      const std::string msg = std::string(KB200_NS_STR "::RangePolicy bound type error: an unsafe implicit conversion is performed on a bound (") +
+                              std::to_string(bound) + "), which may not preserve its original value.\n";
+      Impl::policy_abort(msg.c_str());
     }
     return static_cast<index_type>(bound);
   }
@@ -161,12 +194,14 @@ class MDRangePolicy {
   using work_tag = typename traits::tag;
   using launch_bounds = typename traits::bounds;
   using index_type = typename Impl::index_of<typename traits::index>::type;
-  using point_type = std::array<index_type, rank>;
-  using tile_type = std::array<index_type, rank>;
+  using point_type = Array<index_type, rank>;
+  using tile_type = Array<index_type, rank>;
   // device iteration is Left/Left like the reference's Cuda backend (Cuda/Kokkos_Cuda_MDRangePolicy.hpp:25-35):
   // dimension 0 is the fastest-varying one and maps to threadIdx.x
   static constexpr Iterate outer_direction = Iterate::Left, inner_direction = Iterate::Left;
 
+  MDRangePolicy() = default;
+  // braced lists of one element type: {0, 0, 0}, {n0, n1, n2} [, {t0, t1, t2}]
   template <class L, class U>
   MDRangePolicy(std::initializer_list<L> lower, std::initializer_list<U> upper) { init(lower, upper, std::initializer_list<index_type>{}); }
   template <class L, class U, class Tl>
@@ -175,45 +210,102 @@ class MDRangePolicy {
   MDRangePolicy(const B200& s, std::initializer_list<L> lower, std::initializer_list<U> upper) : m_space(s) { init(lower, upper, std::initializer_list<index_type>{}); }
   template <class L, class U, class Tl>
   MDRangePolicy(const B200& s, std::initializer_list<L> lower, std::initializer_list<U> upper, std::initializer_list<Tl> tile) : m_space(s) { init(lower, upper, tile); }
+  // point_type / tile_type (also what a double-braced {{0, 1}} or a list of mixed integer types binds to)
   MDRangePolicy(const point_type& lower, const point_type& upper, const tile_type& tile = tile_type{}) { init_arrays(lower, upper, tile); }
   // (template on the space type: a braced list such as {{0, 0, 0}} must never be considered for the execution-space parameter)
   template <class S, class = std::enable_if_t<std::is_same<std::decay_t<S>, B200>::value>>
   MDRangePolicy(const S& s, const point_type& lower, const point_type& upper, const tile_type& tile = tile_type{}) : m_space(s) { init_arrays(lower, upper, tile); }
+  // Array of any integer type; the tile may name fewer dimensions than the rank (KokkosExp_MDRangePolicy.hpp:262-310,
+  // core/unit_test/TestMDRangePolicyConstructors.hpp:38-77)
+  template <class LT, size_t LN, class UT, size_t UN, class TT = index_type, size_t TN = (size_t)rank,
+            class = std::enable_if_t<!(std::is_same<LT, index_type>::value && std::is_same<UT, index_type>::value && std::is_same<TT, index_type>::value &&
+                                       TN == (size_t)rank)>>
+  MDRangePolicy(const Array<LT, LN>& lower, const Array<UT, UN>& upper, const Array<TT, TN>& tile = Array<TT, TN>{}) {
+    init_arrays(to_point(lower, "lower"), to_point(upper, "upper"), to_tile(tile));
+  }
+  template <class S, class LT, size_t LN, class UT, size_t UN, class TT = index_type, size_t TN = (size_t)rank,
+            class = std::enable_if_t<std::is_same<std::decay_t<S>, B200>::value &&
+                                     !(std::is_same<LT, index_type>::value && std::is_same<UT, index_type>::value && std::is_same<TT, index_type>::value &&
+                                       TN == (size_t)rank)>>
+  MDRangePolicy(const S& s, const Array<LT, LN>& lower, const Array<UT, UN>& upper, const Array<TT, TN>& tile = Array<TT, TN>{}) : m_space(s) {
+    init_arrays(to_point(lower, "lower"), to_point(upper, "upper"), to_tile(tile));
+  }
 
   const B200& space() const { return m_space; }
   point_type m_lower{}, m_upper{};
   tile_type m_tile{}, m_tile_end{};
   index_type m_num_tiles = 0, m_prod_tile_dims = 1;
+  bool m_tune_tile_size = false;
   static constexpr int max_tile_product = 1024;  // one tile = one thread block
+  int max_total_tile_size() const { return Impl::get_tile_size_properties(m_space).max_total_tile_size; }
+  bool impl_tune_tile_size() const { return m_tune_tile_size; }
+  // the tile the policy would pick on its own for these extents (KokkosExp_MDRangePolicy.hpp:335-352)
+  tile_type tile_size_recommended() const {
+    const Impl::TileSizeProperties pr = Impl::get_tile_size_properties(m_space);
+    tile_type rec{};
+    for (int d = 0; d < rank; ++d) rec[d] = d == 0 ? (index_type)pr.default_largest_tile_size : (index_type)pr.default_tile_size;
+    return rec;
+  }
 
  private:
+  template <class T>
+  static index_type checked(const T bound, int dim) {
+    if (Impl::index_conversion_unsafe<index_type>(bound)) {
+      const std::string msg = std::string(KB200_NS_STR "::MDRangePolicy bound type error: an unsafe implicit conversion is performed on a bound (") +
+                              std::to_string(bound) + ") in dimension (" + std::to_string(dim) + "), which may not preserve its original value.\n";
+      Impl::policy_abort(msg.c_str());
+    }
+    return static_cast<index_type>(bound);
+  }
+  template <class T, size_t N>
+  static point_type to_point(const Array<T, N>& a, const char*) {
+    static_assert(N == (size_t)rank, "kb200::MDRangePolicy: bound arrays must have one entry per dimension");
+    point_type p{};
+    for (int d = 0; d < rank; ++d) p[d] = checked(a[d], d);
+    return p;
+  }
+  template <class T, size_t N>
+  static tile_type to_tile(const Array<T, N>& a) {
+    static_assert(N <= (size_t)rank, "kb200::MDRangePolicy: the tile array has more entries than the policy has dimensions");
+    tile_type t{};
+    if constexpr (N > 0)
+      for (size_t d = 0; d < N; ++d) t[d] = checked(a[d], (int)d);
+    return t;
+  }
   template <class L, class U, class Tl>
   void init(std::initializer_list<L> lo, std::initializer_list<U> up, std::initializer_list<Tl> tl) {
     if ((int)lo.size() != rank || (int)up.size() != rank || ((int)tl.size() != rank && tl.size() != 0))
-      Impl::policy_abort("kb200::MDRangePolicy: Constructor initializer lists have wrong size");
+      Impl::policy_abort(KB200_NS_STR "::MDRangePolicy: Constructor initializer lists have wrong size");
     point_type l{}, u{};
     tile_type t{};
-    int k = 0; for (auto v : lo) l[k++] = (index_type)v;
-    k = 0; for (auto v : up) u[k++] = (index_type)v;
-    k = 0; for (auto v : tl) t[k++] = (index_type)v;
+    int k = 0; for (auto v : lo) { l[k] = checked(v, k); ++k; }
+    k = 0; for (auto v : up) { u[k] = checked(v, k); ++k; }
+    k = 0; for (auto v : tl) { t[k] = checked(v, k); ++k; }
     init_arrays(l, u, t);
   }
   void init_arrays(const point_type& l, const point_type& u, const tile_type& t) {
     m_lower = l; m_upper = u; m_tile = t;
-    // defaults (B200): 32 threads along the contiguous dimension, then 4, 2, 1...: one warp = one 256-byte row
-    static constexpr int dflt[6] = {32, 4, 2, 1, 1, 1};
+    const Impl::TileSizeProperties pr = Impl::get_tile_size_properties(m_space);
     m_num_tiles = 1; m_prod_tile_dims = 1;
     for (int d = 0; d < rank; ++d) {
-      if (m_upper[d] < m_lower[d]) Impl::policy_abort("kb200::MDRangePolicy bounds error: The lower bound is greater than its upper bound");
+      if (m_upper[d] < m_lower[d]) {
+        const std::string msg = std::string(KB200_NS_STR "::MDRangePolicy bounds error: The lower bound (") + std::to_string(m_lower[d]) +
+                                ") is greater than its upper bound (" + std::to_string(m_upper[d]) + ") in dimension " + std::to_string(d) + ".\n";
+        Impl::policy_abort(msg.c_str());
+      }
       const index_type len = m_upper[d] - m_lower[d];
-      if (m_tile[d] <= 0) m_tile[d] = dflt[d];
-      if (m_tile[d] > len && len > 0) m_tile[d] = len;
+      if (m_tile[d] <= 0) {  // default: see TileSizeProperties
+        m_tune_tile_size = true;
+        if (d == 0) m_tile[d] = (index_type)pr.default_largest_tile_size;
+        else m_tile[d] = (long long)m_prod_tile_dims * pr.default_tile_size < (long long)pr.max_total_tile_size ? (index_type)pr.default_tile_size : (index_type)1;
+      }
+      if (m_tile[d] > len && len > 0) m_tile[d] = len;  // no idle threads along a short dimension
       if (m_tile[d] < 1) m_tile[d] = 1;
       m_tile_end[d] = (len + m_tile[d] - 1) / m_tile[d];
       m_num_tiles *= m_tile_end[d];
       m_prod_tile_dims *= m_tile[d];
     }
-    if (m_prod_tile_dims > max_tile_product) Impl::policy_abort("kb200::MDRangePolicy: tile dimensions exceed the maximum of 1024 threads per tile");
+    if (m_prod_tile_dims > (index_type)max_tile_product) Impl::policy_abort(KB200_NS_STR "::MDRangePolicy: tile dimensions exceed the maximum of 1024 threads per tile");
   }
   B200 m_space;
 };

@@ -520,6 +520,7 @@ __global__ void team_reduce_kernel(const __grid_constant__ F f, const __grid_con
                                    const ReduceScratch scratch) {
   using V = typename Red::value_type;
   extern __shared__ __align__(16) unsigned char smem[];
+  if (p.league_size <= 0) return reduce_store_identity(red, scratch);
   V acc;
   red.init(acc);
   for (int lr = blockIdx.x; lr < p.league_size; lr += gridDim.x) {

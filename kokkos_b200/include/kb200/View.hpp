@@ -84,10 +84,10 @@ template <class D> struct data_type_dynamic_rank { static constexpr int value = 
 template <class D> struct data_type_dynamic_rank<D*> { static constexpr int value = 1 + data_type_dynamic_rank<D>::value; };
 template <class D, size_t N> struct data_type_dynamic_rank<D[N]> { static constexpr int value = data_type_dynamic_rank<D>::value; };
 // static extent of dimension r (0 = dynamic); for D = T*..*[N1][N2] the static dimensions are the trailing ones, outermost first
-template <class D> struct data_type_static { static constexpr size_t get(int) { return 0; } };
-template <class D> struct data_type_static<D*> { static constexpr size_t get(int r) { return data_type_static<D>::get(r); } };
+template <class D> struct data_type_static { KB200_FUNCTION static constexpr size_t get(int) { return 0; } };
+template <class D> struct data_type_static<D*> { KB200_FUNCTION static constexpr size_t get(int r) { return data_type_static<D>::get(r); } };
 template <class D, size_t N> struct data_type_static<D[N]> {
-  static constexpr size_t get(int r) {  // r counts static dimensions from the outermost
+  KB200_FUNCTION static constexpr size_t get(int r) {  // r counts static dimensions from the outermost
     return r == 0 ? N : data_type_static<D>::get(r - 1);
   }
 };
@@ -228,10 +228,8 @@ class View {
     const size_t ix[sizeof...(Is)] = {(size_t)is...};
     size_t off = 0;
     if constexpr (std::is_same<array_layout, LayoutLeft>::value) {
-#pragma unroll
-      for (int r = rank - 1; r >= 0; --r) off = off * m_ext[r] + ix[r];
+      for (int r = rank - 1; r >= 0; --r) off = off * m_ext[r] + ix[r];  // (constant trip count: unrolled)
     } else {
-#pragma unroll
       for (int r = 0; r < rank; ++r) off = off * m_ext[r] + ix[r];
     }
     return ref(off);

@@ -155,6 +155,22 @@ KB200_DEVICE_FUNCTION void reduce_signal_host(const ReduceScratch& s) {
   }
 }
 
+// An EMPTY iteration range: the result is init() -> final() with no join at all.  A user reducer's join need not be neutral
+// on identities (core/unit_test/TestReduceCombinatorical.hpp:27-45 adds 1 per join and expects exactly 0 for N = 0), so the
+// kernels return through here instead of combining per-thread identities.  Launched with one block.
+template <class Red>
+KB200_DEVICE_FUNCTION void reduce_store_identity(const Red& red, const ReduceScratch& s) {
+  using V = typename Red::value_type;
+  if (threadIdx.x + threadIdx.y + threadIdx.z == 0 && blockIdx.x == 0) {
+    V v;
+    red.init(v);
+    red.final(v);
+    if (s.result0) *reinterpret_cast<V*>(s.result0) = v;
+    if (s.result1) *reinterpret_cast<V*>(s.result1) = v;
+    reduce_signal_host(s);
+  }
+}
+
 // All threads of every block must call this (it contains barriers).  `v` is meaningful in
 // thread 0 (the block's partial).  Red additionally provides init(value_type&) and
 // final(value_type&).

@@ -92,6 +92,7 @@ __global__ void mdrange_reduce_kernel(const __grid_constant__ F f, const __grid_
                                       const __grid_constant__ MDParams<RANK, Index> p, const ReduceScratch scratch) {
   using V = typename Red::value_type;
   __shared__ __align__(16) unsigned char smem[32 * sizeof(V)];
+  if (p.num_tiles <= 0) return reduce_store_identity(red, scratch);
   V acc;
   red.init(acc);
   md_walk<RANK, C, Index>(p, [&](const Index* idx) { md_invoke<Tag>(f, idx, std::make_index_sequence<RANK>{}, acc); });

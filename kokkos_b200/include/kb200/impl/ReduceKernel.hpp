@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
                         const ReduceScratch scratch) {
   using V = typename Red::value_type;
   __shared__ __align__(16) unsigned char smem[32 * sizeof(V)];
+  if (n_units <= 0 && body.edge_count() <= 0) return reduce_store_identity(red, scratch);  // (grid is one block then)
   V acc;
   red.init(acc);
 

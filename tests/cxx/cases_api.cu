@@ -585,3 +585,93 @@ int kb200_case_views(i64 n, i64* out) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ Array, MDRangePolicy from Arrays, result-less reduce, user reducer
+namespace {
+struct FinalWritesView {  // TestReduceCombinatorical.hpp:262-300: no result argument, final() stores on the device
+  View<i64> result;
+  View<const i64*> x;
+  KB200_INLINE_FUNCTION void operator()(const i64 i, i64& u) const { u += x(i); }
+  KB200_INLINE_FUNCTION void final(i64& u) const { result() = u + 7; }
+};
+template <class Space>
+struct PlainSum {  // a user-written reducer: the memory space of result_view_type says where the result lives
+  using reducer = PlainSum;
+  using value_type = i64;
+  using result_view_type = View<i64, Space, MemoryTraits<Unmanaged>>;
+  result_view_type result;
+  explicit PlainSum(i64* r) : result(r) {}
+  KB200_INLINE_FUNCTION void join(i64& d, const i64& s) const { d += s; }
+  KB200_INLINE_FUNCTION void init(i64& v) const { v = 0; }
+  KB200_INLINE_FUNCTION i64& reference() const { return *result.data(); }
+  KB200_INLINE_FUNCTION result_view_type view() const { return result; }
+};
+struct JoinAddsOne {  // TestReduceCombinatorical.hpp:27-56 (AddPlus)
+  using reducer = JoinAddsOne;
+  using value_type = i64;
+  using result_view_type = View<i64, HostSpace, MemoryTraits<Unmanaged>>;
+  result_view_type result;
+  explicit JoinAddsOne(i64* r) : result(r) {}
+  KB200_INLINE_FUNCTION void join(i64& d, const i64& s) const { d += s + 1; }
+  KB200_INLINE_FUNCTION void init(i64& v) const { v = 0; }
+  KB200_INLINE_FUNCTION i64& reference() const { return *result.data(); }
+  KB200_INLINE_FUNCTION result_view_type view() const { return result; }
+};
+}  // namespace
+
+extern "C" {
+int kb200_case_utilities(const i64* hx, i64 n, i64* out) {
+  return guarded([&] {
+    auto x = to_device(hx, n);
+    View<const i64*> xc = x;
+    // out[0]: result-less parallel_reduce(n, functor) and (policy, functor)
+    View<i64> r("r");
+    parallel_reduce(n, FinalWritesView{r, xc});
+    i64 h = 0;
+    deep_copy(h, r);
+    out[0] = h;
+    parallel_reduce("labelled", RangePolicy<>(1, n), FinalWritesView{r, xc});
+    deep_copy(h, r);
+    out[1] = h;
+    // out[2..3]: user reducer with a host result, then a device result
+    i64 host_sum = -1;
+    parallel_reduce(n, KB200_LAMBDA(const i64 i, i64& u) { u += xc(i); }, PlainSum<HostSpace>(&host_sum));
+    out[2] = host_sum;
+    View<i64> dsum("dsum");
+    parallel_reduce(n, KB200_LAMBDA(const i64 i, i64& u) { u += 2 * xc(i); }, PlainSum<B200Space>(dsum.data()));
+    deep_copy(h, dsum);
+    out[3] = h;
+    // out[4..7]: MDRangePolicy built from Arrays of another integer type, tile naming only the first dimension
+    using Pol = MDRangePolicy<Rank<3>>;
+    Pol p(Array<int, 3>{{1, 2, 3}}, Array<int, 3>{{41, 22, 13}}, Array<int, 1>{{8}});
+    out[4] = p.m_tile[0] * 10000 + p.m_tile[1] * 100 + p.m_tile[2];
+    Pol q({0, 0, 0}, {100, 100, 100});
+    const auto rec = q.tile_size_recommended();
+    out[5] = (rec[0] == q.m_tile[0] && rec[1] == q.m_tile[1] && rec[2] == q.m_tile[2]) ? (i64)(rec[0] * rec[1] * rec[2]) : -1;
+    out[6] = q.max_total_tile_size();
+    i64 cnt = 0;
+    parallel_reduce(p, KB200_LAMBDA(const i64 i, const i64 j, const i64 k, i64& u) { u += i + 100 * j + 10000 * k; }, cnt);
+    out[7] = cnt;
+    // out[8]: Array / kokkos_swap / numbers on the device
+    i64 bad = 0;
+    parallel_reduce(64, KB200_LAMBDA(const i64 i, i64& u) {
+      Array<i64, 3> a{{i, i + 1, i + 2}}, b{{-i, -i - 1, -i - 2}};
+      kokkos_swap(a, b);
+      i64 c[2] = {1, 2}, d[2] = {3, 4};
+      kokkos_swap(c, d);
+      auto [a0, a1, a2] = a;
+      if (a0 != -i || a1 != -i - 1 || a2 != -i - 2 || b[2] != i + 2 || c[0] != 3 || d[1] != 2 || a.size() != 3 || !(a != b)) ++u;
+      if (numbers::pi_v<float> != 3.14159265358979323846f || numbers::sqrt2 * numbers::sqrt2 < 1.999999 || numbers::inv_pi * numbers::pi > 1.000001) ++u;
+    }, bad);
+    out[8] = bad;
+    // out[9..11]: an empty range is init() -> final() with no join, for every policy kind (the join here is not neutral)
+    i64 e0 = -1, e1 = -1, e2 = -1;
+    parallel_reduce(RangePolicy<>(5, 5), KB200_LAMBDA(const i64, i64& u) { u += 1; }, JoinAddsOne(&e0));
+    parallel_reduce(MDRangePolicy<Rank<2>>({0, 0}, {0, 9}), KB200_LAMBDA(const i64, const i64, i64& u) { u += 1; }, JoinAddsOne(&e1));
+    parallel_reduce(TeamPolicy<>(0, AUTO), KB200_LAMBDA(const TeamPolicy<>::member_type&, i64& u) { u += 1; }, JoinAddsOne(&e2));
+    out[9] = e0; out[10] = e1; out[11] = e2;
+    return 0;
+  });
+}
+
+}  // extern "C"

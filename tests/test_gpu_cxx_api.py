@@ -254,3 +254,20 @@ def test_views_deep_copy_subview_mirrors(cases):
     assert out[2] == int((i[2:n - 1] ** 2).sum()) and out[3] == (n - 1) ** 2 and out[4] == 0
     assert out[5] == 5 and out[6] == 7 and out[7] == 1
     assert out[8] == 2048 * 148 and out[9] == 1
+
+
+def test_array_policy_arrays_resultless_reduce_user_reducer(cases):
+    """Kokkos::Array, MDRangePolicy from Arrays (TestMDRangePolicyConstructors.hpp:38-77), parallel_reduce without a result and a
+    user-written reducer whose result_view_type is on the host / device (TestReduceCombinatorical.hpp:27-56,460-490)."""
+    n = 100003
+    x = np.random.default_rng(5).integers(-1000, 1000, n, dtype=np.int64)
+    out = np.zeros(16, dtype=np.int64)
+    ok(cases, cases.kb200_case_utilities(P(x), c_int64(n), P(out)))
+    assert out[0] == int(x.sum()) + 7 and out[1] == int(x[1:].sum()) + 7
+    assert out[2] == int(x.sum()) and out[3] == 2 * int(x.sum())
+    assert out[4] == 8 * 10000 + 4 * 100 + 4           # first dimension as given, the rest the device default
+    assert out[5] == 32 * 4 * 4 and out[6] == 1024
+    i, j, k = np.meshgrid(np.arange(1, 41), np.arange(2, 22), np.arange(3, 13), indexing="ij")
+    assert out[7] == int((i + 100 * j + 10000 * k).sum())
+    assert out[8] == 0
+    assert list(out[9:12]) == [0, 0, 0]                # empty Range / MDRange / Team reduce: identity, no join
