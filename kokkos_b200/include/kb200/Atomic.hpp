@@ -13,14 +13,16 @@
 //     team scratch in shared memory; kernels that know their operand is a View use the *_g forms;
 //   * fetch ops emit `atom.relaxed.gpu[.global].<op>`;
 //   * f64/f32 add, s/u 32/64 min/max, b32/b64 and/or/xor are native; everything else that is
-//     1,2,4 or 8 bytes goes through a CAS loop on the containing word; larger types are
-//     unsupported on this path (the reference's lock-array fallback is not reproduced).
+//     1,2,4 or 8 bytes goes through a CAS loop on the containing word, 16-byte objects (complex<double>)
+//     through the 128-bit CAS, anything larger through an address-hashed spin lock.
 #ifndef KB200_ATOMIC_HPP
 #define KB200_ATOMIC_HPP
 
 #include "Macros.hpp"
 #include <type_traits>
+#include <cstdint>
 #include <cstring>
+#include <mutex>
 
 namespace kb200 {
 namespace Impl {
@@ -113,24 +115,81 @@ KB200_DEVICE_FUNCTION unsigned short atom_cas(unsigned short* p, unsigned short 
   return r;
 }
 
+// 16-byte objects (complex<double>, small structs): one 128-bit compare-and-swap, SASS ATOM.E.CAS.128 (sm_90+).  The reference
+// takes a lock from a hashed lock array for these (desul Lock_Based_Fetch_Op_CUDA.hpp:20-52); no lock is needed here.
+struct alignas(16) Word128 {
+  unsigned long long lo, hi;
+  KB200_DEVICE_FUNCTION bool operator==(const Word128& o) const { return lo == o.lo && hi == o.hi; }
+  KB200_DEVICE_FUNCTION bool operator!=(const Word128& o) const { return !(*this == o); }
+};
+KB200_DEVICE_FUNCTION Word128 atom_cas(Word128* p, Word128 cmp, Word128 val) {
+  Word128 r;
+  asm volatile(
+      "{\n\t.reg .b128 c, v, d;\n\t"
+      "mov.b128 c, {%2, %3};\n\t"
+      "mov.b128 v, {%4, %5};\n\t"
+      "atom.relaxed.gpu.cas.b128 d, [%6], c, v;\n\t"
+      "mov.b128 {%0, %1}, d;\n\t}"
+      : "=l"(r.lo), "=l"(r.hi)
+      : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(p)
+      : "memory");
+  return r;
+}
+
 // the unsigned word type an object of SIZE bytes is operated on as
 template <int SIZE> struct word_of;
 template <> struct word_of<2> { using type = unsigned short; };
 template <> struct word_of<4> { using type = unsigned; };
 template <> struct word_of<8> { using type = unsigned long long; };
+template <> struct word_of<16> { using type = Word128; };
 
 template <class T, class W = typename word_of<sizeof(T)>::type>
 KB200_DEVICE_FUNCTION W as_word(T v) { W w; memcpy(&w, &v, sizeof(T)); return w; }
 template <class T, class W>
 KB200_DEVICE_FUNCTION T from_word(W w) { T v; memcpy(&v, &w, sizeof(T)); return v; }
 
+// Objects that fit no CAS width (more than 16 bytes, or 16 bytes under-aligned): a spin lock picked by hashing the address
+// (the role of desul's lock array, Lock_Array_CUDA.hpp:60-132 + Lock_Based_Fetch_Op_CUDA.hpp:20-52).  The table is a
+// translation-unit-local device array, so two kernels compiled in DIFFERENT translation units must not update the same such
+// object concurrently; within one kernel (the case the reference's tests and real codes have) any thread mix is safe.  The
+// acquire / update / release sequence sits inside one branch of a loop so a warp never spins on a lock held by its own lane.
+static __device__ unsigned kb200_atomic_lock_table[1u << 14];
+template <class T>
+KB200_DEVICE_FUNCTION void volatile_copy(T* dst, const T* src) {
+  if constexpr (sizeof(T) % 8 == 0 && alignof(T) >= 8) {
+    for (unsigned k = 0; k < sizeof(T) / 8; ++k)
+      reinterpret_cast<volatile unsigned long long*>(dst)[k] = reinterpret_cast<const volatile unsigned long long*>(src)[k];
+  } else {
+    for (unsigned k = 0; k < sizeof(T); ++k) reinterpret_cast<volatile unsigned char*>(dst)[k] = reinterpret_cast<const volatile unsigned char*>(src)[k];
+  }
+}
+template <class T, class F>
+KB200_DEVICE_FUNCTION T locked_rmw(T* p, F f) {
+  const unsigned long long a = reinterpret_cast<unsigned long long>(p);
+  unsigned* lock = &kb200_atomic_lock_table[((a >> 4) ^ (a >> 18)) & ((1u << 14) - 1)];
+  T before;
+  bool done = false;
+  while (!done) {
+    if (atomicCAS(lock, 0u, 1u) == 0u) {
+      __threadfence();
+      volatile_copy(&before, p);  // (L1-bypassing: another SM may have written the object under the same lock)
+      const T after = f(before);
+      volatile_copy(p, &after);
+      __threadfence();
+      atomicExch(lock, 0u);
+      done = true;
+    }
+  }
+  return before;
+}
+
 // generic RMW through compare-and-swap (desul Lock_Free_Fetch_Op.hpp:23-55 plays this role);
 // returns the value before the update.  1-byte objects use the enclosing aligned 16-bit word.
 template <class T, class F>
 KB200_DEVICE_FUNCTION T cas_loop(T* p, F f) {
-  static_assert(sizeof(T) == 1 || sizeof(T) == 2 || sizeof(T) == 4 || sizeof(T) == 8,
-                "kb200 atomics support 1,2,4,8-byte types (no lock-array fallback)");
-  if constexpr (sizeof(T) == 1) {
+  if constexpr (!(sizeof(T) == 1 || sizeof(T) == 2 || sizeof(T) == 4 || sizeof(T) == 8 || (sizeof(T) == 16 && alignof(T) >= 16))) {
+    return locked_rmw(p, f);
+  } else if constexpr (sizeof(T) == 1) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
     unsigned short* wp = reinterpret_cast<unsigned short*>(a & ~uintptr_t(1));
     const int shift = (a & 1) * 8;
@@ -150,7 +209,9 @@ KB200_DEVICE_FUNCTION T cas_loop(T* p, F f) {
   } else {
     using W = typename word_of<sizeof(T)>::type;
     W* wp = reinterpret_cast<W*>(p);
-    W old = *reinterpret_cast<volatile W*>(wp), assumed;
+    W old, assumed;
+    if constexpr (sizeof(T) == 16) old = atom_cas(wp, W{0, 0}, W{0, 0});  // an atomic 128-bit read: swaps 0 for 0 or fails
+    else old = *reinterpret_cast<volatile W*>(wp);
     do {
       assumed = old;
       old = atom_cas(wp, assumed, as_word<T>(f(from_word<T, W>(assumed))));
@@ -263,7 +324,7 @@ KB200_DEVICE_FUNCTION T atomic_exchange(T* p, T v) {
 }
 template <class T>
 KB200_DEVICE_FUNCTION T atomic_compare_exchange(T* p, T compare, T v) {
-  if constexpr (sizeof(T) == 2 || sizeof(T) == 4 || sizeof(T) == 8) {
+  if constexpr (sizeof(T) == 2 || sizeof(T) == 4 || sizeof(T) == 8 || sizeof(T) == 16) {
     using W = typename Impl::word_of<sizeof(T)>::type;
     return Impl::from_word<T, W>(Impl::atom_cas(reinterpret_cast<W*>(p), Impl::as_word<T>(compare), Impl::as_word<T>(v)));
   } else {
@@ -272,8 +333,12 @@ KB200_DEVICE_FUNCTION T atomic_compare_exchange(T* p, T compare, T v) {
 }
 template <class T>
 KB200_DEVICE_FUNCTION T atomic_load(const T* p) {
-  static_assert(sizeof(T) <= 8, "");
-  if constexpr (sizeof(T) == 8) {
+  if constexpr (sizeof(T) > 8 && !(sizeof(T) == 16 && alignof(T) >= 16)) {
+    return Impl::locked_rmw(const_cast<T*>(p), [](const T& o) { return o; });
+  } else if constexpr (sizeof(T) == 16) {
+    using W = Impl::Word128;
+    return Impl::from_word<T, W>(Impl::atom_cas(reinterpret_cast<W*>(const_cast<T*>(p)), W{0, 0}, W{0, 0}));
+  } else if constexpr (sizeof(T) == 8) {
     unsigned long long w;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
     return Impl::from_word<T, unsigned long long>(w);
@@ -287,8 +352,9 @@ KB200_DEVICE_FUNCTION T atomic_load(const T* p) {
 }
 template <class T>
 KB200_DEVICE_FUNCTION void atomic_store(T* p, T v) {
-  static_assert(sizeof(T) <= 8, "");
-  if constexpr (sizeof(T) == 8) {
+  if constexpr (sizeof(T) > 8) {
+    (void)Impl::cas_loop(p, [=](const T&) { return v; });
+  } else if constexpr (sizeof(T) == 8) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(Impl::as_word<T>(v)) : "memory");
   } else if constexpr (sizeof(T) == 4) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(Impl::as_word<T>(v)) : "memory");
@@ -304,12 +370,35 @@ KB200_DEVICE_FUNCTION void atomic_store(T* p, T v) {
 // __host__ __device__ like Kokkos::atomic_* (they are called from KB200_LAMBDA functors).  The device pass is the
 // PTX above; the host pass (host-space Views in host code) uses the compiler's __atomic builtins.
 namespace Impl {
+// objects the host has no lock-free instruction for (more than 8 bytes): address-striped mutexes, shared by all translation units
+template <class T> constexpr bool host_lock_free = sizeof(T) <= 8 && (sizeof(T) & (sizeof(T) - 1)) == 0;
+inline std::mutex& host_atomic_mutex(const void* p) {
+  static std::mutex table[64];
+  return table[(reinterpret_cast<uintptr_t>(p) >> 4) & 63];
+}
 template <class T, class F>
 inline T host_rmw(T* p, F f) {
-  T old, nw;
-  __atomic_load(p, &old, __ATOMIC_RELAXED);
-  do { nw = f(old); } while (!__atomic_compare_exchange(p, &old, &nw, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
-  return old;
+  if constexpr (host_lock_free<T>) {
+    T old, nw;
+    __atomic_load(p, &old, __ATOMIC_RELAXED);
+    do { nw = f(old); } while (!__atomic_compare_exchange(p, &old, &nw, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    return old;
+  } else {
+    std::lock_guard<std::mutex> guard(host_atomic_mutex(p));
+    T old = *p;
+    *p = f(old);
+    return old;
+  }
+}
+template <class T>
+inline T host_load(const T* p) {
+  if constexpr (host_lock_free<T>) { T v; __atomic_load(p, &v, __ATOMIC_RELAXED); return v; }
+  else { std::lock_guard<std::mutex> guard(host_atomic_mutex(p)); return *p; }
+}
+template <class T>
+inline void host_store(T* p, const T& v) {
+  if constexpr (host_lock_free<T>) { T w = v; __atomic_store(p, &w, __ATOMIC_RELAXED); }
+  else { std::lock_guard<std::mutex> guard(host_atomic_mutex(p)); *p = v; }
 }
 }  // namespace Impl
 #ifdef __CUDA_ARCH__
@@ -353,11 +442,11 @@ KB200_FORCEINLINE_FUNCTION T atomic_compare_exchange(T* p, std::common_type_t<T>
 }
 template <class T>
 KB200_FORCEINLINE_FUNCTION T atomic_load(const T* p) {
-  KB200_ATOMIC_DISPATCH(return Impl::dev::atomic_load(p);, T v; __atomic_load(p, &v, __ATOMIC_RELAXED); return v;)
+  KB200_ATOMIC_DISPATCH(return Impl::dev::atomic_load(p);, return Impl::host_load(p);)
 }
 template <class T>
 KB200_FORCEINLINE_FUNCTION void atomic_store(T* p, std::common_type_t<T> v) {
-  KB200_ATOMIC_DISPATCH(Impl::dev::atomic_store(p, v);, __atomic_store(p, &v, __ATOMIC_RELAXED);)
+  KB200_ATOMIC_DISPATCH(Impl::dev::atomic_store(p, v);, Impl::host_store(p, (const T&)v);)
 }
 
 // op_fetch forms (return the NEW value) and the remaining fetch_op forms of the desul wrapper

@@ -210,6 +210,24 @@ constexpr None_t None{};
 template <class Policy, class Property>
 inline Policy require(const Policy& p, Property) { return p; }
 }  // namespace Experimental
+// reduction identities of the 16-bit floating types, from their bit patterns (core/src/Kokkos_Half_NumericTraits.hpp:40-230)
+template <>
+struct reduction_identity<__half> {
+  KB200_FORCEINLINE_FUNCTION static __half bits(unsigned short b) { __half_raw r; r.x = b; return __half(r); }
+  KB200_FORCEINLINE_FUNCTION static __half sum() { return bits(0x0000); }
+  KB200_FORCEINLINE_FUNCTION static __half prod() { return bits(0x3C00); }
+  KB200_FORCEINLINE_FUNCTION static __half max() { return bits(0xFBFF); }  // -65504
+  KB200_FORCEINLINE_FUNCTION static __half min() { return bits(0x7BFF); }  // +65504
+};
+template <>
+struct reduction_identity<__nv_bfloat16> {
+  KB200_FORCEINLINE_FUNCTION static __nv_bfloat16 bits(unsigned short b) { __nv_bfloat16_raw r; r.x = b; return __nv_bfloat16(r); }
+  KB200_FORCEINLINE_FUNCTION static __nv_bfloat16 sum() { return bits(0x0000); }
+  KB200_FORCEINLINE_FUNCTION static __nv_bfloat16 prod() { return bits(0x3F80); }
+  KB200_FORCEINLINE_FUNCTION static __nv_bfloat16 max() { return bits(0xFF7F); }
+  KB200_FORCEINLINE_FUNCTION static __nv_bfloat16 min() { return bits(0x7F7F); }
+};
+
 namespace Impl {
 template <class T>
 struct TypeInfo { static std::string name() { return typeid(T).name(); } };  // core/src/impl/Kokkos_TypeInfo.hpp

@@ -19,6 +19,7 @@
 #define KB200_REDUCERS_HPP
 
 #include "Macros.hpp"
+#include "Complex.hpp"
 #include "impl/Collectives.hpp"
 #include <cfloat>
 #include <climits>
@@ -75,6 +76,11 @@ struct reduction_identity<bool> {
 KB200_IDENTITY_FP(float, FLT_MAX)
 KB200_IDENTITY_FP(double, DBL_MAX)
 #undef KB200_IDENTITY_FP
+template <class T>
+struct reduction_identity<complex<T>> {  // core/src/Kokkos_Complex.hpp:905-925
+  KB200_FORCEINLINE_FUNCTION constexpr static complex<T> sum() noexcept { return complex<T>(reduction_identity<T>::sum(), reduction_identity<T>::sum()); }
+  KB200_FORCEINLINE_FUNCTION constexpr static complex<T> prod() noexcept { return complex<T>(reduction_identity<T>::prod(), reduction_identity<T>::sum()); }
+};
 
 // ---------------------------------------------------------------- value structs
 template <class Scalar, class Index>

@@ -1,14 +1,14 @@
 // kb200/View.hpp -- View<T*>-style device allocations for the B200 execution space.
 //
 // Covers what the hot path needs of core/src/Kokkos_View.hpp + core/src/Cuda/Kokkos_CudaSpace.{hpp,cpp}:
-//   * View<T>, View<T*> ... View<T******>  (rank 0..6, run-time extents), LayoutLeft / LayoutRight,
+//   * View<T>, View<T*> ... View<T********>  (rank 0..8, run-time extents), LayoutLeft / LayoutRight,
 //     memory spaces B200Space (device, CudaSpace::allocate -> b200_malloc) and HostSpace,
 //     MemoryTraits<Unmanaged> / pointer-wrapping constructors, labels, ref-counted ownership
 //     (impl/Kokkos_SharedAlloc.*), zero-initialisation at allocation (View/Kokkos_ViewAlloc.hpp:100-166 ->
 //     ZeroMemset<B200> = b200_memset_async + fence), WithoutInitializing;
 //   * deep_copy between spaces / from a scalar, create_mirror_view[_and_copy], subview of rank-1 ranges.
 // Device Views default to LayoutLeft as in the reference's Cuda backend (first index fastest).
-// Everything rank>6, strided layouts, static extents and DualView/DynRankView are out of scope
+// Strided layouts, static extents and DualView/DynRankView are out of scope
 // (SURVEY.md section 2 rows 11, 24).
 #ifndef KB200_VIEW_HPP
 #define KB200_VIEW_HPP
@@ -138,7 +138,7 @@ class View {
 
  public:
   static constexpr int rank = Impl::data_type_rank<DataType>::value;
-  static_assert(rank <= 6, "kb200::View supports rank 0..6");
+  static_assert(rank <= 8, "kb200::View supports rank 0..8");
   using value_type = typename Impl::data_type_rank<DataType>::type;
   using non_const_value_type = std::remove_const_t<value_type>;
   using memory_space = std::conditional_t<std::is_void<typename props::space>::value, B200Space, typename props::space>;
@@ -153,23 +153,24 @@ class View {
   static constexpr bool is_managed = !(props::traits & Unmanaged);
   static constexpr bool is_device = !std::is_same<memory_space, HostSpace>::value;
   using HostMirror = View<std::remove_const_t<DataType>, array_layout, HostSpace>;
+  using traits = View;  // View::traits::memory_space, ::array_layout, ::value_type ... (the reference's ViewTraits members)
   using non_const_type = View<DataType, Props...>;
 
-  KB200_INLINE_FUNCTION View() : m_data(nullptr), m_rec(nullptr) { for (int r = 0; r < 6; ++r) m_ext[r] = 0; }
+  KB200_INLINE_FUNCTION View() : m_data(nullptr), m_rec(nullptr) { for (int r = 0; r < 8; ++r) m_ext[r] = 0; }
 
   // allocating constructors
-  explicit View(const std::string& label, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) { allocate(ViewAllocProp{label, true, nullptr}, n0, n1, n2, n3, n4, n5); }
-  explicit View(const char* label, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) { allocate(ViewAllocProp{label, true, nullptr}, n0, n1, n2, n3, n4, n5); }
-  explicit View(const ViewAllocProp& p, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) { allocate(p, n0, n1, n2, n3, n4, n5); }
+  explicit View(const std::string& label, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0, size_t n6 = 0, size_t n7 = 0) { allocate(ViewAllocProp{label, true, nullptr}, n0, n1, n2, n3, n4, n5, n6, n7); }
+  explicit View(const char* label, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0, size_t n6 = 0, size_t n7 = 0) { allocate(ViewAllocProp{label, true, nullptr}, n0, n1, n2, n3, n4, n5, n6, n7); }
+  explicit View(const ViewAllocProp& p, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0, size_t n6 = 0, size_t n7 = 0) { allocate(p, n0, n1, n2, n3, n4, n5, n6, n7); }
   // wrapping (unmanaged) constructor
-  KB200_INLINE_FUNCTION View(pointer_type ptr, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) : m_data(ptr), m_rec(nullptr) {
-    set_extents(n0, n1, n2, n3, n4, n5);
+  KB200_INLINE_FUNCTION View(pointer_type ptr, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0, size_t n6 = 0, size_t n7 = 0) : m_data(ptr), m_rec(nullptr) {
+    set_extents(n0, n1, n2, n3, n4, n5, n6, n7);
   }
 
   // View over team/thread scratch memory: View<T*, ScratchSpace, Unmanaged>(team.team_scratch(level), n)
   template <class S, class = typename S::is_scratch_tag>
-  KB200_INLINE_FUNCTION View(const S& scratch, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) : m_rec(nullptr) {
-    set_extents(n0, n1, n2, n3, n4, n5);
+  KB200_INLINE_FUNCTION View(const S& scratch, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0, size_t n6 = 0, size_t n7 = 0) : m_rec(nullptr) {
+    set_extents(n0, n1, n2, n3, n4, n5, n6, n7);
     m_data = static_cast<pointer_type>(scratch.get_shmem_aligned(size() * sizeof(value_type), (ptrdiff_t)scratch_value_alignment));
   }
   // scratch Views are aligned to max(sizeof(T), alignof(T), 8) and shmem_size() reserves that much slack
@@ -181,8 +182,8 @@ class View {
     for (int r = 0; r < rank; ++r) n *= l.dimension[r];
     return n * sizeof(value_type) + scratch_value_alignment;
   }
-  static constexpr size_t shmem_size(size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) {
-    return (rank > 0 ? n0 : 1) * (rank > 1 ? n1 : 1) * (rank > 2 ? n2 : 1) * (rank > 3 ? n3 : 1) * (rank > 4 ? n4 : 1) * (rank > 5 ? n5 : 1) * sizeof(value_type) + scratch_value_alignment;
+  static constexpr size_t shmem_size(size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0, size_t n6 = 0, size_t n7 = 0) {
+    return (rank > 0 ? n0 : 1) * (rank > 1 ? n1 : 1) * (rank > 2 ? n2 : 1) * (rank > 3 ? n3 : 1) * (rank > 4 ? n4 : 1) * (rank > 5 ? n5 : 1) * (rank > 6 ? n6 : 1) * (rank > 7 ? n7 : 1) * sizeof(value_type) + scratch_value_alignment;
   }
 
   KB200_INLINE_FUNCTION View(const View& o) : m_data(o.m_data), m_rec(o.m_rec) { copy_ext(o); retain(); }
@@ -191,7 +192,7 @@ class View {
   template <class D2, class... P2, class = std::enable_if_t<std::is_convertible<typename View<D2, P2...>::pointer_type, pointer_type>::value &&
                                                             View<D2, P2...>::rank == rank>>
   KB200_INLINE_FUNCTION View(const View<D2, P2...>& o) : m_data(o.data()), m_rec(is_managed ? o.impl_record() : nullptr) {
-    for (int r = 0; r < 6; ++r) m_ext[r] = o.extent(r);
+    for (int r = 0; r < 8; ++r) m_ext[r] = o.extent(r);
     retain();
   }
   KB200_INLINE_FUNCTION View& operator=(const View& o) {
@@ -222,7 +223,7 @@ class View {
     else return ref((size_t)i2 + m_ext[2] * ((size_t)i1 + m_ext[1] * (size_t)i0));
   }
 
-  // rank 4..6: generic mixed-radix offset (LayoutLeft: first index fastest; LayoutRight: last index fastest)
+  // rank 4..8: generic mixed-radix offset (LayoutLeft: first index fastest; LayoutRight: last index fastest)
   template <class... Is, int R = rank, std::enable_if_t<(R >= 4) && sizeof...(Is) == (size_t)R, int> = 0>
   KB200_FORCEINLINE_FUNCTION reference_type operator()(const Is... is) const {
     const size_t ix[sizeof...(Is)] = {(size_t)is...};
@@ -260,14 +261,15 @@ class View {
     if constexpr (is_atomic) return reference_type(m_data + off);
     else return m_data[off];
   }
-  KB200_INLINE_FUNCTION void set_extents(size_t n0, size_t n1, size_t n2, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) {
+  KB200_INLINE_FUNCTION void set_extents(size_t n0, size_t n1, size_t n2, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0, size_t n6 = 0, size_t n7 = 0) {
     m_ext[0] = rank > 0 ? n0 : 1; m_ext[1] = rank > 1 ? n1 : 1; m_ext[2] = rank > 2 ? n2 : 1;
     m_ext[3] = rank > 3 ? n3 : 1; m_ext[4] = rank > 4 ? n4 : 1; m_ext[5] = rank > 5 ? n5 : 1;
+    m_ext[6] = rank > 6 ? n6 : 1; m_ext[7] = rank > 7 ? n7 : 1;
     // static extents occupy the dimensions after the dynamic ones
     constexpr int dyn = Impl::data_type_dynamic_rank<DataType>::value;
     for (int r = dyn; r < rank; ++r) m_ext[r] = Impl::data_type_static<DataType>::get(r - dyn);
   }
-  KB200_INLINE_FUNCTION void copy_ext(const View& o) { for (int r = 0; r < 6; ++r) m_ext[r] = o.m_ext[r]; }
+  KB200_INLINE_FUNCTION void copy_ext(const View& o) { for (int r = 0; r < 8; ++r) m_ext[r] = o.m_ext[r]; }
   KB200_INLINE_FUNCTION void retain() {
 #ifndef __CUDA_ARCH__
     if (m_rec) __atomic_add_fetch(&m_rec->refcount, 1, __ATOMIC_RELAXED);
@@ -278,9 +280,9 @@ class View {
     if (m_rec) { Impl::release(m_rec); m_rec = nullptr; }
 #endif
   }
-  void allocate(const ViewAllocProp& p, size_t n0, size_t n1, size_t n2, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0) {
+  void allocate(const ViewAllocProp& p, size_t n0, size_t n1, size_t n2, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0, size_t n6 = 0, size_t n7 = 0) {
     static_assert(!std::is_const<value_type>::value, "cannot allocate a View of const");
-    set_extents(n0, n1, n2, n3, n4, n5);
+    set_extents(n0, n1, n2, n3, n4, n5, n6, n7);
     const size_t bytes = size() * sizeof(value_type);
     m_rec = new Impl::AllocRecord();
     m_rec->label = p.label;
@@ -313,7 +315,7 @@ class View {
   }
 
   pointer_type m_data;
-  size_t m_ext[6];
+  size_t m_ext[8];
   Impl::AllocRecord* m_rec;
 };
 
@@ -392,14 +394,14 @@ struct DeepCopy {
 
 template <class D, class... P>
 typename View<D, P...>::HostMirror create_mirror_view(const View<D, P...>& v) {
-  return typename View<D, P...>::HostMirror(view_alloc(WithoutInitializing, v.label() + "_mirror"), v.extent(0), v.extent(1), v.extent(2), v.extent(3), v.extent(4), v.extent(5));
+  return typename View<D, P...>::HostMirror(view_alloc(WithoutInitializing, v.label() + "_mirror"), v.extent(0), v.extent(1), v.extent(2), v.extent(3), v.extent(4), v.extent(5), v.extent(6), v.extent(7));
 }
 template <class D, class... P>
 typename View<D, P...>::HostMirror create_mirror(const View<D, P...>& v) { return create_mirror_view(v); }
 template <class Space, class D, class... P>
 auto create_mirror_view_and_copy(const Space&, const View<D, P...>& v) {
   using Dst = View<std::remove_const_t<D>, typename View<D, P...>::array_layout, typename Space::memory_space>;
-  Dst d(view_alloc(WithoutInitializing, v.label() + "_copy"), v.extent(0), v.extent(1), v.extent(2), v.extent(3), v.extent(4), v.extent(5));
+  Dst d(view_alloc(WithoutInitializing, v.label() + "_copy"), v.extent(0), v.extent(1), v.extent(2), v.extent(3), v.extent(4), v.extent(5), v.extent(6), v.extent(7));
   deep_copy(d, v);
   return d;
 }
