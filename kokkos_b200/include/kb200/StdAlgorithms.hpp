@@ -19,8 +19,64 @@
 #include "Parallel.hpp"
 #include <limits>
 #include <string>
+#include <utility>
 
 namespace kb200 {
+
+// ---------------------------------------------------------------- ViewCopy for strided / layout-changing pairs
+// (core/src/Kokkos_CopyViews.hpp:300-560 ViewCopy).  The index box is flattened with the dimension of smallest destination
+// stride running fastest, so the writes of a warp are contiguous whenever the destination has a unit-stride dimension.
+namespace Impl {
+template <int R>
+struct StridedBox {
+  size_t ext[R > 0 ? R : 1], dst_stride[R > 0 ? R : 1], src_stride[R > 0 ? R : 1];
+  KB200_INLINE_FUNCTION void offsets(size_t flat, size_t& od, size_t& os) const {
+    od = 0; os = 0;
+    for (int r = 0; r < R; ++r) {
+      const size_t c = flat % ext[r];
+      flat /= ext[r];
+      od += c * dst_stride[r];
+      os += c * src_stride[r];
+    }
+  }
+};
+template <class V1, class V2>
+StridedBox<V1::rank> make_strided_box(const V1& dst, const V2& src) {
+  constexpr int R = V1::rank;
+  StridedBox<R> b;
+  int order[R > 0 ? R : 1];
+  for (int r = 0; r < R; ++r) order[r] = r;
+  for (int i = 1; i < R; ++i)  // insertion sort by destination stride
+    for (int j = i; j > 0 && dst.stride(order[j]) < dst.stride(order[j - 1]); --j) std::swap(order[j], order[j - 1]);
+  for (int r = 0; r < R; ++r) { b.ext[r] = dst.extent(order[r]); b.dst_stride[r] = dst.stride(order[r]); b.src_stride[r] = src.stride(order[r]); }
+  return b;
+}
+template <class V1, class V2>
+void strided_copy(const B200& space, const V1& dst, const V2& src) {
+  using T = typename V1::non_const_value_type;
+  const size_t n = dst.size();
+  if (n == 0) return;
+  const StridedBox<V1::rank> box = make_strided_box(dst, src);
+  T* dp = const_cast<T*>(dst.data());
+  const T* sp = src.data();
+  if constexpr (V1::is_device && V2::is_device) {
+    parallel_for("kb200::ViewCopy", RangePolicy<>(space, 0, (long long)n), KB200_LAMBDA(const long long i) {
+      size_t od, os;
+      box.offsets((size_t)i, od, os);
+      dp[od] = sp[os];
+    });
+  } else if constexpr (!V1::is_device && !V2::is_device) {
+    space.fence("kb200::deep_copy(host strided view, host view)");
+    for (size_t i = 0; i < n; ++i) {
+      size_t od, os;
+      box.offsets(i, od, os);
+      dp[od] = sp[os];
+    }
+  } else {
+    throw std::runtime_error("kb200::deep_copy: a strided or layout-changing copy between host and device needs a contiguous mirror on one side");
+  }
+}
+}  // namespace Impl
 
 // ---------------------------------------------------------------- ViewFill: deep_copy(view, value)
 // (core/src/Kokkos_CopyViews.hpp:58-300 ViewFill; zero bit patterns take the memset path like ZeroMemset<Cuda>)
@@ -31,6 +87,23 @@ void deep_copy(const B200& space, const View<D, P...>& dst, const typename View<
   const size_t n = dst.size();
   if (n == 0) return;
   T* p = const_cast<T*>(dst.data());
+  if constexpr (V::is_strided) {  // fill element by element through the strides
+    if (!dst.span_is_contiguous()) {
+      const Impl::StridedBox<V::rank> box = Impl::make_strided_box(dst, dst);
+      const T v = value;
+      if constexpr (V::is_device) {
+        parallel_for("kb200::ViewFill", RangePolicy<>(space, 0, (long long)n), KB200_LAMBDA(const long long i) {
+          size_t od, os;
+          box.offsets((size_t)i, od, os);
+          p[od] = v;
+        });
+      } else {
+        space.fence("kb200::deep_copy(host view, value)");
+        for (size_t i = 0; i < n; ++i) { size_t od, os; box.offsets(i, od, os); p[od] = v; }
+      }
+      return;
+    }
+  }
   if constexpr (V::is_device) {
     bool all_zero = true;
     const unsigned char* b = reinterpret_cast<const unsigned char*>(&value);

@@ -23,8 +23,10 @@ namespace kb200 {
 
 struct LayoutLeft {};
 struct LayoutRight {};
-// LayoutStride: only the extent bookkeeping used for scratch sizing (View<..., LayoutStride>::shmem_size(order_dimensions(...)),
-// core/src/Kokkos_Layout.hpp:148-230); strided element access is outside the hot path
+// LayoutStride (core/src/Kokkos_Layout.hpp:148-230): explicit per-dimension strides.  Views of this layout come out of
+// multi-dimensional subview() and carry their strides; they are also what scratch sizing (shmem_size(order_dimensions(...))) takes.
+struct ALL_t {};
+constexpr ALL_t ALL{};
 struct LayoutStride {
   size_t dimension[8] = {1, 1, 1, 1, 1, 1, 1, 1};
   size_t stride[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -99,7 +101,7 @@ template <> struct view_props<> {
 template <class First, class... Rest>
 struct view_props<First, Rest...> {
   using next = view_props<Rest...>;
-  static constexpr bool is_layout = std::is_same<First, LayoutLeft>::value || std::is_same<First, LayoutRight>::value;
+  static constexpr bool is_layout = std::is_same<First, LayoutLeft>::value || std::is_same<First, LayoutRight>::value || std::is_same<First, LayoutStride>::value;
   static constexpr bool is_space = std::is_same<First, HostSpace>::value || std::is_same<First, B200Space>::value ||
                                    std::is_same<First, B200HostPinnedSpace>::value || std::is_same<First, B200>::value ||
                                    std::is_same<First, ScratchMemorySpace<B200>>::value;
@@ -132,8 +134,15 @@ inline void release(AllocRecord* r) {
 }
 }  // namespace Impl
 
+namespace Impl {
+// only LayoutStride Views pay for stride storage (empty base otherwise)
+template <bool Strided> struct ViewStrides {};
+template <> struct ViewStrides<true> { size_t m_stride[8] = {0, 0, 0, 0, 0, 0, 0, 0}; };
+template <class... Props> struct view_is_strided : std::is_same<typename view_props<Props...>::layout, LayoutStride> {};
+}  // namespace Impl
+
 template <class DataType, class... Props>
-class View {
+class View : public Impl::ViewStrides<Impl::view_is_strided<Props...>::value> {
   using props = Impl::view_props<Props...>;
 
  public:
@@ -152,6 +161,7 @@ class View {
   using reference_type = std::conditional_t<is_atomic, AtomicDataElement<value_type>, value_type&>;
   static constexpr bool is_managed = !(props::traits & Unmanaged);
   static constexpr bool is_device = !std::is_same<memory_space, HostSpace>::value;
+  static constexpr bool is_strided = std::is_same<array_layout, LayoutStride>::value;
   using HostMirror = View<std::remove_const_t<DataType>, array_layout, HostSpace>;
   using traits = View;  // View::traits::memory_space, ::array_layout, ::value_type ... (the reference's ViewTraits members)
   using non_const_type = View<DataType, Props...>;
@@ -209,17 +219,22 @@ class View {
   template <int R = rank, std::enable_if_t<R == 0, int> = 0>
   KB200_FORCEINLINE_FUNCTION reference_type operator()() const { return ref(0); }
   template <class I0, int R = rank, std::enable_if_t<R == 1, int> = 0>
-  KB200_FORCEINLINE_FUNCTION reference_type operator()(const I0 i0) const { return ref((size_t)i0); }
+  KB200_FORCEINLINE_FUNCTION reference_type operator()(const I0 i0) const {
+    if constexpr (is_strided) return ref((size_t)i0 * this->m_stride[0]);
+    else return ref((size_t)i0);
+  }
   template <class I0, int R = rank, std::enable_if_t<R == 1, int> = 0>
-  KB200_FORCEINLINE_FUNCTION reference_type operator[](const I0 i0) const { return ref((size_t)i0); }
+  KB200_FORCEINLINE_FUNCTION reference_type operator[](const I0 i0) const { return (*this)(i0); }
   template <class I0, class I1, int R = rank, std::enable_if_t<R == 2, int> = 0>
   KB200_FORCEINLINE_FUNCTION reference_type operator()(const I0 i0, const I1 i1) const {
-    if constexpr (std::is_same<array_layout, LayoutLeft>::value) return ref((size_t)i0 + m_ext[0] * (size_t)i1);
+    if constexpr (is_strided) return ref((size_t)i0 * this->m_stride[0] + (size_t)i1 * this->m_stride[1]);
+    else if constexpr (std::is_same<array_layout, LayoutLeft>::value) return ref((size_t)i0 + m_ext[0] * (size_t)i1);
     else return ref((size_t)i1 + m_ext[1] * (size_t)i0);
   }
   template <class I0, class I1, class I2, int R = rank, std::enable_if_t<R == 3, int> = 0>
   KB200_FORCEINLINE_FUNCTION reference_type operator()(const I0 i0, const I1 i1, const I2 i2) const {
-    if constexpr (std::is_same<array_layout, LayoutLeft>::value) return ref((size_t)i0 + m_ext[0] * ((size_t)i1 + m_ext[1] * (size_t)i2));
+    if constexpr (is_strided) return ref((size_t)i0 * this->m_stride[0] + (size_t)i1 * this->m_stride[1] + (size_t)i2 * this->m_stride[2]);
+    else if constexpr (std::is_same<array_layout, LayoutLeft>::value) return ref((size_t)i0 + m_ext[0] * ((size_t)i1 + m_ext[1] * (size_t)i2));
     else return ref((size_t)i2 + m_ext[2] * ((size_t)i1 + m_ext[1] * (size_t)i0));
   }
 
@@ -228,7 +243,9 @@ class View {
   KB200_FORCEINLINE_FUNCTION reference_type operator()(const Is... is) const {
     const size_t ix[sizeof...(Is)] = {(size_t)is...};
     size_t off = 0;
-    if constexpr (std::is_same<array_layout, LayoutLeft>::value) {
+    if constexpr (is_strided) {
+      for (int r = 0; r < rank; ++r) off += ix[r] * this->m_stride[r];
+    } else if constexpr (std::is_same<array_layout, LayoutLeft>::value) {
       for (int r = rank - 1; r >= 0; --r) off = off * m_ext[r] + ix[r];  // (constant trip count: unrolled)
     } else {
       for (int r = 0; r < rank; ++r) off = off * m_ext[r] + ix[r];
@@ -244,17 +261,37 @@ class View {
     for (int r = 0; r < rank; ++r) s *= m_ext[r];
     return s;
   }
-  KB200_FORCEINLINE_FUNCTION size_t span() const { return size(); }
-  KB200_FORCEINLINE_FUNCTION constexpr bool span_is_contiguous() const { return true; }
+  KB200_FORCEINLINE_FUNCTION size_t span() const {
+    if constexpr (is_strided) {
+      size_t last = 0;
+      for (int r = 0; r < rank; ++r) { if (m_ext[r] == 0) return 0; last += (m_ext[r] - 1) * this->m_stride[r]; }
+      return last + 1;
+    } else {
+      return size();
+    }
+  }
+  KB200_FORCEINLINE_FUNCTION bool span_is_contiguous() const { return span() == size(); }
   KB200_FORCEINLINE_FUNCTION bool is_allocated() const { return m_data != nullptr; }
   KB200_FORCEINLINE_FUNCTION size_t stride(int r) const {
-    if (std::is_same<array_layout, LayoutLeft>::value) { size_t s = 1; for (int k = 0; k < r; ++k) s *= m_ext[k]; return s; }
+    if constexpr (is_strided) return this->m_stride[r];
+    else if (std::is_same<array_layout, LayoutLeft>::value) { size_t s = 1; for (int k = 0; k < r; ++k) s *= m_ext[k]; return s; }
     size_t s = 1; for (int k = rank - 1; k > r; --k) s *= m_ext[k]; return s;
   }
   std::string label() const { return m_rec ? m_rec->label : std::string(); }
   int use_count() const { return m_rec ? m_rec->refcount : 0; }
   KB200_INLINE_FUNCTION Impl::AllocRecord* impl_record() const { return m_rec; }
   void impl_window(size_t offset, size_t count) { m_data += offset; m_ext[0] = count; }
+  // subview construction: share `parent`'s allocation record, point at `ptr`, take extents (and strides) as given
+  template <class Parent>
+  void impl_assign_strided(const Parent& parent, pointer_type ptr, const size_t* ext, const size_t* strides) {
+    drop();
+    m_data = ptr;
+    m_rec = is_managed ? parent.impl_record() : nullptr;
+    for (int r = 0; r < 8; ++r) m_ext[r] = r < rank ? ext[r] : 1;
+    if constexpr (is_strided)
+      for (int r = 0; r < 8; ++r) this->m_stride[r] = r < rank ? strides[r] : 0;
+    retain();
+  }
 
  private:
   KB200_FORCEINLINE_FUNCTION reference_type ref(size_t off) const {
@@ -268,8 +305,16 @@ class View {
     // static extents occupy the dimensions after the dynamic ones
     constexpr int dyn = Impl::data_type_dynamic_rank<DataType>::value;
     for (int r = dyn; r < rank; ++r) m_ext[r] = Impl::data_type_static<DataType>::get(r - dyn);
+    if constexpr (is_strided) {  // built from extents alone: contiguous, first index fastest
+      size_t st = 1;
+      for (int r = 0; r < rank; ++r) { this->m_stride[r] = st; st *= m_ext[r]; }
+    }
   }
-  KB200_INLINE_FUNCTION void copy_ext(const View& o) { for (int r = 0; r < 8; ++r) m_ext[r] = o.m_ext[r]; }
+  KB200_INLINE_FUNCTION void copy_ext(const View& o) {
+    for (int r = 0; r < 8; ++r) m_ext[r] = o.m_ext[r];
+    if constexpr (is_strided)
+      for (int r = 0; r < 8; ++r) this->m_stride[r] = o.m_stride[r];
+  }
   KB200_INLINE_FUNCTION void retain() {
 #ifndef __CUDA_ARCH__
     if (m_rec) __atomic_add_fetch(&m_rec->refcount, 1, __ATOMIC_RELAXED);
@@ -334,8 +379,57 @@ View<D, P...> subview(const View<D, P...>& v, const std::pair<I0, I1>& r) {
   return s;
 }
 
+// ---------------------------------------------------------------- subview, general form (core/src/Kokkos_View.hpp subview / ViewMapping)
+// One argument per dimension: an index (the dimension is dropped), a pair [begin, end) or ALL.  The result is a LayoutStride
+// View of the kept dimensions sharing the parent's allocation.
+namespace Impl {
+template <class T, int K> struct add_pointers { using type = typename add_pointers<T, K - 1>::type*; };
+template <class T> struct add_pointers<T, 0> { using type = T; };
+template <class A> struct subview_arg_keeps : std::integral_constant<int, std::is_integral<std::decay_t<A>>::value ? 0 : 1> {};
+template <class A>
+inline void subview_arg(const A& a, size_t extent, size_t& begin, size_t& count, bool& keep) {
+  if constexpr (std::is_integral<A>::value) { begin = (size_t)a; count = 1; keep = false; if (begin >= extent) throw std::runtime_error("kb200::subview: index out of bounds"); }
+  else if constexpr (std::is_same<A, ALL_t>::value) { begin = 0; count = extent; keep = true; }
+  else {
+    begin = (size_t)a.first; count = (size_t)a.second >= begin ? (size_t)a.second - begin : 0; keep = true;
+    if ((size_t)a.second > extent || (size_t)a.first > (size_t)a.second) throw std::runtime_error("kb200::subview: range out of bounds");
+  }
+}
+template <class V> struct view_space_of { using type = typename V::memory_space; };
+}  // namespace Impl
+
+template <class D, class... P, class A0, class A1, class... As>
+auto subview(const View<D, P...>& v, const A0& a0, const A1& a1, const As&... as) {
+  using V = View<D, P...>;
+  static_assert(V::rank == 2 + (int)sizeof...(As), "kb200::subview: one argument per dimension");
+  constexpr int kept = Impl::subview_arg_keeps<A0>::value + Impl::subview_arg_keeps<A1>::value + (0 + ... + Impl::subview_arg_keeps<As>::value);
+  using SubData = typename Impl::add_pointers<typename V::value_type, kept>::type;
+  using Sub = std::conditional_t<V::is_managed, View<SubData, LayoutStride, typename V::memory_space>,
+                                 View<SubData, LayoutStride, typename V::memory_space, MemoryTraits<Unmanaged>>>;
+  size_t begin[8] = {0}, count[8] = {0};
+  bool keep[8] = {false};
+  int r = 0;
+  Impl::subview_arg(a0, v.extent(0), begin[0], count[0], keep[0]);
+  Impl::subview_arg(a1, v.extent(1), begin[1], count[1], keep[1]);
+  r = 2;
+  ((Impl::subview_arg(as, v.extent(r), begin[r], count[r], keep[r]), ++r), ...);
+  size_t off = 0, ext[8] = {1, 1, 1, 1, 1, 1, 1, 1}, str[8] = {0};
+  int k = 0;
+  for (int d = 0; d < V::rank; ++d) {
+    off += begin[d] * v.stride(d);
+    if (keep[d]) { ext[k] = count[d]; str[k] = v.stride(d); ++k; }
+  }
+  Sub sub;
+  sub.impl_assign_strided(v, v.data() + off, ext, str);
+  return sub;
+}
+
 // ---------------------------------------------------------------- deep_copy
 namespace Impl {
+// element-wise copy for strided or layout-changing pairs (defined in StdAlgorithms.hpp, after parallel_for)
+template <class V1, class V2>
+void strided_copy(const B200& space, const V1& dst, const V2& src);
+
 template <class DstSpace, class SrcSpace>
 inline void copy_bytes(const B200& space, void* dst, const void* src, size_t bytes) {
   constexpr bool dd = !std::is_same<DstSpace, HostSpace>::value && !std::is_same<DstSpace, B200HostPinnedSpace>::value;
@@ -355,10 +449,16 @@ void deep_copy(const B200& space, const View<D1, P1...>& dst, const View<D2, P2.
   using V1 = View<D1, P1...>; using V2 = View<D2, P2...>;
   static_assert(std::is_same<typename V1::non_const_value_type, typename V2::non_const_value_type>::value, "deep_copy: value types differ");
   static_assert(V1::rank == V2::rank, "deep_copy: ranks differ");
-  static_assert(V1::rank <= 1 || std::is_same<typename V1::array_layout, typename V2::array_layout>::value,
-                "deep_copy: layouts differ (no transposing copy on this path)");
   for (int r = 0; r < V1::rank; ++r)
     if (dst.extent(r) != src.extent(r)) throw std::runtime_error("kb200::deep_copy: extents differ");
+  // strided operands or different layouts: element-wise ViewCopy kernel (Kokkos_CopyViews.hpp:300-560); otherwise one memcpy
+  if constexpr (V1::is_strided || V2::is_strided || (V1::rank > 1 && !std::is_same<typename V1::array_layout, typename V2::array_layout>::value)) {
+    if (!(V1::is_strided == V2::is_strided && std::is_same<typename V1::array_layout, typename V2::array_layout>::value && dst.span_is_contiguous() &&
+          src.span_is_contiguous() && !V1::is_strided)) {
+      Impl::strided_copy(space, dst, src);
+      return;
+    }
+  }
   Impl::copy_bytes<typename V1::memory_space, typename V2::memory_space>(space, (void*)dst.data(), (const void*)src.data(),
                                                                          dst.size() * sizeof(typename V1::value_type));
 }

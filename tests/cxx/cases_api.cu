@@ -674,4 +674,49 @@ int kb200_case_utilities(const i64* hx, i64 n, i64* out) {
   });
 }
 
+// ------------------------------------------------------------------ multi-dimensional subviews (LayoutStride), strided ViewCopy / ViewFill
+int kb200_case_strided_subview(i64 n0, i64 n1, i64 n2, i64* out) {
+  return guarded([&] {
+    View<i64***> a("a", (size_t)n0, (size_t)n1, (size_t)n2);
+    parallel_for(MDRangePolicy<Rank<3>>({0, 0, 0}, {n0, n1, n2}), KB200_LAMBDA(const i64 i, const i64 j, const i64 k) { a(i, j, k) = i + 100 * j + 10000 * k; });
+    const i64 jfix = n1 / 2;
+    auto sub = subview(a, std::make_pair((i64)1, n0 - 1), jfix, ALL);  // rank 2: (n0-2) x n2, strides (1, n0*n1)
+    out[0] = (i64)sub.extent(0) * 1000 + (i64)sub.extent(1);
+    out[1] = (i64)sub.stride(0) * 1000000 + (i64)sub.stride(1);
+    out[2] = sub.span_is_contiguous() ? 1 : 0;
+    out[3] = a.use_count();
+    i64 bad = 0;
+    parallel_reduce(MDRangePolicy<Rank<2>>({0, 0}, {(i64)sub.extent(0), (i64)sub.extent(1)}),
+                    KB200_LAMBDA(const i64 i, const i64 k, i64& u) { if (sub(i, k) != (i + 1) + 100 * jfix + 10000 * k) ++u; }, bad);
+    out[4] = bad;
+    // strided -> contiguous copy on the device, then to the host
+    View<i64**> dense("dense", sub.extent(0), sub.extent(1));
+    deep_copy(dense, sub);
+    auto hd = create_mirror_view_and_copy(HostSpace(), dense);
+    i64 bad2 = 0;
+    for (size_t i = 0; i < hd.extent(0); ++i)
+      for (size_t k = 0; k < hd.extent(1); ++k)
+        if (hd(i, k) != (i64)(i + 1) + 100 * jfix + 10000 * (i64)k) ++bad2;
+    out[5] = bad2;
+    // strided fill touches the window only; contiguous -> strided copy writes it back
+    deep_copy(sub, (i64)-7);
+    i64 cnt = 0;
+    parallel_reduce(MDRangePolicy<Rank<3>>({0, 0, 0}, {n0, n1, n2}), KB200_LAMBDA(const i64 i, const i64 j, const i64 k, i64& u) { if (a(i, j, k) == -7) ++u; }, cnt);
+    out[6] = cnt;
+    deep_copy(sub, dense);
+    i64 bad3 = 0;
+    parallel_reduce(MDRangePolicy<Rank<3>>({0, 0, 0}, {n0, n1, n2}), KB200_LAMBDA(const i64 i, const i64 j, const i64 k, i64& u) { if (a(i, j, k) != i + 100 * j + 10000 * k) ++u; }, bad3);
+    out[7] = bad3;
+    // a rank-1 column out of a rank-2 LayoutRight view: stride = row length
+    View<i64**, LayoutRight> m("m", 6, 9);
+    parallel_for(MDRangePolicy<Rank<2>>({0, 0}, {6, 9}), KB200_LAMBDA(const i64 i, const i64 j) { m(i, j) = 10 * i + j; });
+    auto col = subview(m, ALL, 4);
+    i64 colsum = 0;
+    parallel_reduce(col.extent(0), KB200_LAMBDA(const i64 i, i64& u) { u += col(i); }, colsum);
+    out[8] = colsum;
+    out[9] = (i64)col.stride(0);
+    return 0;
+  });
+}
+
 }  // extern "C"

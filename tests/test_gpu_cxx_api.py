@@ -271,3 +271,15 @@ def test_array_policy_arrays_resultless_reduce_user_reducer(cases):
     assert out[7] == int((i + 100 * j + 10000 * k).sum())
     assert out[8] == 0
     assert list(out[9:12]) == [0, 0, 0]                # empty Range / MDRange / Team reduce: identity, no join
+
+
+def test_strided_subview_copy_fill(cases):
+    """subview(view, range, index, ALL) -> LayoutStride View sharing the allocation; element-wise ViewCopy / ViewFill through strides
+    (Kokkos_CopyViews.hpp:300-560; TestMDRange_g.hpp:41-72 is the reference's use)."""
+    n0, n1, n2 = 37, 11, 23
+    out = np.zeros(16, dtype=np.int64)
+    ok(cases, cases.kb200_case_strided_subview(c_int64(n0), c_int64(n1), c_int64(n2), P(out)))
+    assert out[0] == (n0 - 2) * 1000 + n2 and out[1] == 1 * 1000000 + n0 * n1 and out[2] == 0 and out[3] == 2
+    assert out[4] == 0 and out[5] == 0
+    assert out[6] == (n0 - 2) * n2 and out[7] == 0
+    assert out[8] == sum(10 * i + 4 for i in range(6)) and out[9] == 9
