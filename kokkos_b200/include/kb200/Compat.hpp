@@ -199,14 +199,14 @@ namespace Experimental {
 using half_t = __half;          // core/src/Kokkos_Half_FloatingPointWrapper.hpp (sm_100 has native fp16 / bf16)
 using bhalf_t = __nv_bfloat16;
 // Kokkos::Experimental::require(policy, WorkItemProperty): launch hints; accepted and ignored on this backend
-namespace WorkItemProperty {
-struct HintLightWeight_t {};
-struct HintHeavyWeight_t {};
-struct None_t {};
-constexpr HintLightWeight_t HintLightWeight{};
-constexpr HintHeavyWeight_t HintHeavyWeight{};
-constexpr None_t None{};
-}  // namespace WorkItemProperty
+struct WorkItemProperty {  // (a class with constant members, as in the reference, so that `using Experimental::WorkItemProperty;` works)
+  struct HintLightWeight_t {};
+  struct HintHeavyWeight_t {};
+  struct None_t {};
+  static constexpr HintLightWeight_t HintLightWeight{};
+  static constexpr HintHeavyWeight_t HintHeavyWeight{};
+  static constexpr None_t None{};
+};
 template <class Policy, class Property>
 inline Policy require(const Policy& p, Property) { return p; }
 }  // namespace Experimental

@@ -161,7 +161,13 @@ void parallel_for(const std::string& /*label*/, const RangePolicy<P...>& policy,
   // the hardware scheduler balances uneven iterations.  B200 probe, copy lambda 2^28 (profiles/r01_for_probe.log): one element
   // per thread (the reference's mapping) 3.7 TB/s, 256x4 plain 5.59, 256x4 persistent 5.82.
   constexpr bool dynamic = std::is_same<typename Policy::schedule_type, Schedule<Dynamic>>::value;
-  Impl::throw_on_error(Impl::RangeForLaunch<Body, 256, 4>::run(policy.space().impl_instance(), body, n, dynamic ? 0 : 8));
+  using Launch = Impl::RangeForLaunch<Body, 256, 4>;
+  int cap = dynamic ? 0 : 8;
+  if constexpr (Policy::experimental_contains_desired_occupancy) {  // Experimental::prefer(policy, DesiredOccupancy{p})
+    cap = policy.impl_occupancy_cap(Launch::resident_blocks_per_sm());
+    if (!dynamic && cap > 8) cap = 8;
+  }
+  Impl::throw_on_error(Launch::run(policy.space().impl_instance(), body, n, cap));
 }
 template <class... P, class F>
 void parallel_for(const RangePolicy<P...>& policy, const F& f) { parallel_for(std::string(), policy, f); }
@@ -197,7 +203,10 @@ void reduce_dispatch(const RangePolicy<P...>& policy, const F& f, const Red& red
   // __launch_bounds__(256, 4): caps the kernel at 64 registers so >= 1024 threads stay resident per SM.  Without it the
   // 32-byte MinMaxLoc kernels took 142 registers (shuffle trees of the epilogue), one CTA per SM, 12 % occupancy and
   // 3.2 TB/s (profiles/r01_reduce_minmaxloc_ncu.txt); the hot loop itself needs < 48.
-  throw_on_error(RangeReduceLaunch<Body, Red, 256, UNROLL, 4>::run(policy.space().impl_instance(), body, red, n, t.host, t.dev));
+  using Launch = RangeReduceLaunch<Body, Red, 256, UNROLL, 4>;
+  int cap = 0;
+  if constexpr (Policy::experimental_contains_desired_occupancy) cap = policy.impl_occupancy_cap(Launch::resident_blocks_per_sm());
+  throw_on_error(Launch::run(policy.space().impl_instance(), body, red, n, t.host, t.dev, cap));
 }
 template <class... P, class F, class Red>
 void reduce_dispatch(const MDRangePolicy<P...>& policy, const F& f, const Red& red, ResultTarget<typename Red::value_type> t) {

@@ -20,6 +20,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <tuple>
 #include <initializer_list>
 #include <type_traits>
 
@@ -39,6 +40,21 @@ enum class Iterate { Default, Left, Right };
 template <unsigned N, Iterate OuterDir = Iterate::Default, Iterate InnerDir = Iterate::Default>
 struct Rank { static constexpr int rank = (int)N; static constexpr Iterate outer_direction = OuterDir, inner_direction = InnerDir; };
 
+namespace Experimental {
+// Occupancy control (core/src/Kokkos_ExecPolicy.hpp:  DesiredOccupancy / MaximizeOccupancy / prefer(); tests:
+// core/unit_test/TestOccupancyControlTrait.hpp, TestCommonPolicyConstructors.hpp).  On this backend every launcher sizes a
+// persistent grid as SMs x resident blocks, so a desired occupancy of p % simply keeps ceil(resident * p / 100) blocks per SM
+// (the reference's Cuda backend pads the launch with dynamic shared memory to the same end, Cuda_KernelLaunch.hpp:160-210).
+struct DesiredOccupancy {
+  int m_occ = 100;
+  DesiredOccupancy() = default;
+  explicit constexpr DesiredOccupancy(int occ) : m_occ(occ < 0 ? 0 : (occ > 100 ? 100 : occ)) {}
+  explicit constexpr operator int() const { return m_occ; }
+  constexpr int value() const { return m_occ; }
+};
+struct MaximizeOccupancy { explicit MaximizeOccupancy() = default; };
+}  // namespace Experimental
+
 struct ParallelForTag {};     // core/src/Kokkos_Core_fwd.hpp: pattern tags for team_size_max / team_size_recommended
 struct ParallelReduceTag {};
 struct ParallelScanTag {};
@@ -53,10 +69,12 @@ template <unsigned A, unsigned B> struct is_launch_bounds<LaunchBounds<A, B>> : 
 template <class T> struct is_rank : std::false_type {};
 template <unsigned N, Iterate A, Iterate B> struct is_rank<Rank<N, A, B>> : std::true_type {};
 template <class T> struct is_exec_space : std::is_same<T, B200> {};
+template <class T> struct is_occupancy : std::integral_constant<bool, std::is_same<T, Experimental::DesiredOccupancy>::value || std::is_same<T, Experimental::MaximizeOccupancy>::value> {};
 
 template <class... P> struct policy_traits;
 template <> struct policy_traits<> {
   using schedule = Schedule<Static>; using index = void; using bounds = LaunchBounds<>; using tag = void; using rank = void;
+  static constexpr bool desired_occupancy = false;
 };
 template <class F, class... R>
 struct policy_traits<F, R...> {
@@ -64,7 +82,8 @@ struct policy_traits<F, R...> {
   // a bare integral type is an index type too (RangePolicy<Space, long>: impl/Kokkos_AnalyzePolicy.hpp:165-190)
   static constexpr bool is_index = is_index_type<F>::value || std::is_integral<F>::value;
   static constexpr bool known = is_schedule<F>::value || is_index || is_launch_bounds<F>::value ||
-                                is_rank<F>::value || is_exec_space<F>::value;
+                                is_rank<F>::value || is_exec_space<F>::value || is_occupancy<F>::value;
+  static constexpr bool desired_occupancy = std::is_same<F, Experimental::DesiredOccupancy>::value || next::desired_occupancy;
   using schedule = std::conditional_t<is_schedule<F>::value, F, typename next::schedule>;
   using index = std::conditional_t<is_index, std::conditional_t<std::is_integral<F>::value, IndexType<F>, F>, typename next::index>;
   using bounds = std::conditional_t<is_launch_bounds<F>::value, F, typename next::bounds>;
@@ -122,12 +141,79 @@ TileSizeProperties get_tile_size_properties(const Space&) {
   if (msg[0] && msg[std::strlen(msg) - 1] != '\n') std::fprintf(stderr, "\n");
   std::abort();
 }
+// Common base of the execution policies (the role of Impl::PolicyTraits, core/src/impl/Kokkos_AnalyzePolicy.hpp:165-190):
+// publishes the analysed traits and stores the desired occupancy only in policy types that carry the trait (empty otherwise).
+template <bool Has> struct OccupancyStorage {};
+template <> struct OccupancyStorage<true> { Experimental::DesiredOccupancy m_desired_occupancy; };
+template <class... Props>
+struct PolicyTraits : OccupancyStorage<policy_traits<Props...>::desired_occupancy> {
+  using analysed = policy_traits<Props...>;
+  static constexpr bool experimental_contains_desired_occupancy = analysed::desired_occupancy;
+  PolicyTraits() = default;
+  PolicyTraits(const PolicyTraits&) = default;
+  PolicyTraits& operator=(const PolicyTraits&) = default;
+  // from a policy with other traits: the occupancy travels when both sides store one
+  template <class... Other>
+  PolicyTraits(const PolicyTraits<Other...>& o) {
+    if constexpr (experimental_contains_desired_occupancy && PolicyTraits<Other...>::experimental_contains_desired_occupancy)
+      this->m_desired_occupancy = o.m_desired_occupancy;
+    (void)o;
+  }
+  template <bool B = experimental_contains_desired_occupancy, class = std::enable_if_t<B>>
+  Experimental::DesiredOccupancy impl_get_desired_occupancy() const { return this->m_desired_occupancy; }
+  template <bool B = experimental_contains_desired_occupancy, class = std::enable_if_t<B>>
+  void impl_set_desired_occupancy(Experimental::DesiredOccupancy occ) { this->m_desired_occupancy = occ; }
+  // resident blocks per SM a launcher should use, given what the kernel allows
+  int impl_occupancy_cap(int resident_blocks_per_sm) const {
+    if constexpr (experimental_contains_desired_occupancy) {
+      const int want = (resident_blocks_per_sm * this->m_desired_occupancy.value() + 99) / 100;
+      return want < 1 ? 1 : (want < resident_blocks_per_sm ? want : resident_blocks_per_sm);
+    } else {
+      return resident_blocks_per_sm;
+    }
+  }
+};
 }  // namespace Impl
+
+namespace Experimental {
+namespace Impl2 {
+template <template <class...> class Policy, class Done, class... Rest> struct without_occupancy;
+template <template <class...> class Policy, class... Done>
+struct without_occupancy<Policy, std::tuple<Done...>> { using type = Policy<Done...>; };
+template <template <class...> class Policy, class... Done, class F, class... Rest>
+struct without_occupancy<Policy, std::tuple<Done...>, F, Rest...>
+    : std::conditional_t<kb200::Impl::is_occupancy<F>::value, without_occupancy<Policy, std::tuple<Done...>, Rest...>,
+                         without_occupancy<Policy, std::tuple<Done..., F>, Rest...>> {};
+}  // namespace Impl2
+// prefer(policy, DesiredOccupancy{p}) / prefer(policy, MaximizeOccupancy{}): a policy of the matching type with the hint applied
+template <template <class...> class Policy, class... Args>
+auto prefer(const Policy<Args...>& p, DesiredOccupancy occ) {
+  if constexpr (Policy<Args...>::experimental_contains_desired_occupancy) {
+    Policy<Args...> q(p);
+    q.impl_set_desired_occupancy(occ);
+    return q;
+  } else {
+    Policy<Args..., DesiredOccupancy> q{p};
+    q.impl_set_desired_occupancy(occ);
+    return q;
+  }
+}
+template <template <class...> class Policy, class... Args>
+auto prefer(const Policy<Args...>& p, MaximizeOccupancy) {
+  if constexpr (Policy<Args...>::experimental_contains_desired_occupancy) {
+    typename Impl2::without_occupancy<Policy, std::tuple<>, Args...>::type q{p};
+    return q;
+  } else {
+    return p;
+  }
+}
+}  // namespace Experimental
 
 // ------------------------------------------------------------------------------------------ RangePolicy
 template <class... Props>
-class RangePolicy {
+class RangePolicy : public Impl::PolicyTraits<Props...> {
   using traits = Impl::policy_traits<Props...>;
+  template <class...> friend class RangePolicy;
 
  public:
   using execution_space = B200;
@@ -139,6 +225,10 @@ class RangePolicy {
   using member_type = index_type;
 
   RangePolicy() : m_begin(0), m_end(0) {}
+  // same range under other traits (what Experimental::prefer / require produce)
+  template <class... Other, class = std::enable_if_t<!std::is_same<RangePolicy<Other...>, RangePolicy>::value>>
+  RangePolicy(const RangePolicy<Other...>& o)
+      : Impl::PolicyTraits<Props...>(static_cast<const Impl::PolicyTraits<Other...>&>(o)), m_space(o.m_space), m_begin((index_type)o.m_begin), m_end((index_type)o.m_end), m_chunk((index_type)o.m_chunk) {}
   // bounds of any integral type: each is checked for a value-preserving conversion to index_type before use
   // (core/src/Kokkos_ExecPolicy.hpp:235-290; core/unit_test/TestRangePolicyConstructors.hpp pins the diagnostics)
   template <class B, class E, class = std::enable_if_t<std::is_convertible<B, index_type>::value && std::is_convertible<E, index_type>::value &&
@@ -182,8 +272,9 @@ class RangePolicy {
 
 // ------------------------------------------------------------------------------------------ MDRangePolicy
 template <class... Props>
-class MDRangePolicy {
+class MDRangePolicy : public Impl::PolicyTraits<Props...> {
   using traits = Impl::policy_traits<Props...>;
+  template <class...> friend class MDRangePolicy;
   static_assert(!std::is_void<typename traits::rank>::value, "kb200::MDRangePolicy needs a Rank<N> property");
 
  public:
@@ -201,6 +292,14 @@ class MDRangePolicy {
   static constexpr Iterate outer_direction = Iterate::Left, inner_direction = Iterate::Left;
 
   MDRangePolicy() = default;
+  template <class... Other, class = std::enable_if_t<!std::is_same<MDRangePolicy<Other...>, MDRangePolicy>::value && MDRangePolicy<Other...>::rank == rank>>
+  MDRangePolicy(const MDRangePolicy<Other...>& o) : Impl::PolicyTraits<Props...>(static_cast<const Impl::PolicyTraits<Other...>&>(o)), m_space(o.m_space) {
+    for (int d = 0; d < rank; ++d) {
+      m_lower[d] = (index_type)o.m_lower[d]; m_upper[d] = (index_type)o.m_upper[d];
+      m_tile[d] = (index_type)o.m_tile[d]; m_tile_end[d] = (index_type)o.m_tile_end[d];
+    }
+    m_num_tiles = (index_type)o.m_num_tiles; m_prod_tile_dims = (index_type)o.m_prod_tile_dims; m_tune_tile_size = o.m_tune_tile_size;
+  }
   // braced lists of one element type: {0, 0, 0}, {n0, n1, n2} [, {t0, t1, t2}]
   template <class L, class U>
   MDRangePolicy(std::initializer_list<L> lower, std::initializer_list<U> upper) { init(lower, upper, std::initializer_list<index_type>{}); }
@@ -319,8 +418,9 @@ inline PerThreadValue PerThread(size_t v) { return PerThreadValue{v}; }
 class B200TeamMember;
 
 template <class... Props>
-class TeamPolicy {
+class TeamPolicy : public Impl::PolicyTraits<Props...> {
   using traits = Impl::policy_traits<Props...>;
+  template <class...> friend class TeamPolicy;
 
  public:
   using execution_space = B200;
@@ -331,6 +431,11 @@ class TeamPolicy {
   using member_type = B200TeamMember;
 
   TeamPolicy() {}
+  template <class... Other, class = std::enable_if_t<!std::is_same<TeamPolicy<Other...>, TeamPolicy>::value>>
+  TeamPolicy(const TeamPolicy<Other...>& o)
+      : Impl::PolicyTraits<Props...>(static_cast<const Impl::PolicyTraits<Other...>&>(o)), m_space(o.m_space), m_league(o.m_league), m_team(o.m_team), m_vec(o.m_vec), m_chunk(o.m_chunk) {
+    for (int l = 0; l < 2; ++l) { m_team_scratch[l] = o.m_team_scratch[l]; m_thread_scratch[l] = o.m_thread_scratch[l]; }
+  }
   TeamPolicy(int league, int team, int vec = 1) : m_league(league), m_team(team), m_vec(vec) { check(); }
   TeamPolicy(int league, const AUTO_t&, int vec = 1) : m_league(league), m_team(-1), m_vec(vec) { check(); }
   TeamPolicy(int league, const AUTO_t&, const AUTO_t&) : m_league(league), m_team(-1), m_vec(-1) { check(); }

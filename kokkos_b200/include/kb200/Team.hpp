@@ -573,6 +573,7 @@ struct TeamShape {
     int bps = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, threads, smem);
     if (bps < 1) bps = 1;
+    bps = pol.impl_occupancy_cap(bps);
     const long long cap = (long long)rt.sm_count() * bps;
     grid = (int)(p.league_size < cap ? (p.league_size > 0 ? p.league_size : 1) : cap);
     p.l1_per_team = (p.l1_team + p.l1_thread * team + 255) & ~(size_t)255;

@@ -156,6 +156,7 @@ struct MDRangeFor {
     int bps = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, sh.threads, 0);
     if (bps < 1) bps = 1;
+    bps = pol.impl_occupancy_cap(bps);
     const long long cap = (long long)rt.sm_count() * bps * 4;  // a few waves: tiles are short
     const int grid = (int)(sh.p.num_tiles < cap ? sh.p.num_tiles : cap);
     sh.set_grid(grid);
@@ -178,6 +179,7 @@ struct MDRangeReduce {
     int bps = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, sh.threads, 0);
     if (bps < 1) bps = 1;
+    bps = pol.impl_occupancy_cap(bps);
     const long long cap = (long long)rt.sm_count() * bps;
     long long tiles = sh.p.num_tiles;
     const int grid = (int)(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
