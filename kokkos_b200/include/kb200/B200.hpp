@@ -81,7 +81,7 @@ class B200 {
   using memory_space = B200Space;
   using device_type = Device<B200, B200Space>;
   using array_layout = LayoutLeft;
-  using size_type = unsigned int;
+  using size_type = long long;  // the default index type of policies on this space (64-bit: no 2^31 special case, Policy.hpp)
   using scratch_memory_space = ScratchMemorySpace<B200>;
 
   // default instance (Kokkos::Cuda()): requires kb200::initialize()

@@ -148,6 +148,11 @@ template <> struct OccupancyStorage<true> { Experimental::DesiredOccupancy m_des
 template <class... Props>
 struct PolicyTraits : OccupancyStorage<policy_traits<Props...>::desired_occupancy> {
   using analysed = policy_traits<Props...>;
+  using execution_space = B200;
+  using schedule_type = typename analysed::schedule;
+  using work_tag = typename analysed::tag;
+  using launch_bounds = typename analysed::bounds;
+  using index_type = typename index_of<typename analysed::index>::type;
   static constexpr bool experimental_contains_desired_occupancy = analysed::desired_occupancy;
   PolicyTraits() = default;
   PolicyTraits(const PolicyTraits&) = default;

@@ -6,9 +6,11 @@
 //     MemoryTraits<Unmanaged> / pointer-wrapping constructors, labels, ref-counted ownership
 //     (impl/Kokkos_SharedAlloc.*), zero-initialisation at allocation (View/Kokkos_ViewAlloc.hpp:100-166 ->
 //     ZeroMemset<B200> = b200_memset_async + fence), WithoutInitializing;
-//   * deep_copy between spaces / from a scalar, create_mirror_view[_and_copy], subview of rank-1 ranges.
+//   * trailing static extents (View<T*[3]>), LayoutStride Views carrying explicit strides;
+//   * deep_copy between spaces / from a scalar (element-wise through strides where needed), create_mirror_view[_and_copy],
+//     subview: rank-1 ranges keep the parent's type, the general form (index / range / ALL per dimension) yields LayoutStride.
 // Device Views default to LayoutLeft as in the reference's Cuda backend (first index fastest).
-// Strided layouts, static extents and DualView/DynRankView are out of scope
+// DualView/DynRankView, mdspan interop, resize/realloc and layout-transposing host<->device copies are out of scope
 // (SURVEY.md section 2 rows 11, 24).
 #ifndef KB200_VIEW_HPP
 #define KB200_VIEW_HPP
