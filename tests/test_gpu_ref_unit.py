@@ -1,7 +1,8 @@
 """The reference's OWN unit tests on the B200 execution space.
 
-tests/ref_unit/Makefile compiles core/unit_test/incremental/Test01...Test17 of the reference UNMODIFIED (from
-/root/reference, with its vendored gtest) against the kb200 layer exposed as `Kokkos::` and links them into
+tests/ref_unit/Makefile compiles the reference test sources named in tests/ref_unit/tests.list (core/unit_test/incremental/*,
+core/unit_test/Test*.hpp, core/unit_test/default/TestDefaultDeviceType_*.cpp) UNMODIFIED, from /root/reference and with its
+vendored gtest, against the kb200 layer exposed as `Kokkos::`, and links them into
 tests/ref_unit/_build/ref_unit_b200 (built in the build container; the binary travels to the GPU box).  This test runs it
 and requires every gtest case to pass."""
 import os
@@ -25,5 +26,5 @@ def test_reference_incremental_unit_tests_pass_on_b200():
     tail = "\n".join(out.splitlines()[-40:])
     assert p.returncode == 0, tail
     m = re.search(r"\[  PASSED  \] (\d+) tests", out)
-    assert m and int(m.group(1)) >= 20, tail
+    assert m and int(m.group(1)) >= 150, tail
     assert "FAILED" not in out, tail
