@@ -24,6 +24,7 @@
 #include "kb200/Parallel.hpp"
 #include "kb200/Team.hpp"
 #include "kb200/TeamMDRange.hpp"
+#include "kb200/UniqueToken.hpp"
 #include "kb200/StdAlgorithms.hpp"
 #include "kb200/Compat.hpp"
 

@@ -494,6 +494,42 @@ struct DeepCopy {
 };
 }  // namespace Impl
 
+// resize(view, n0...) keeps the common index box, realloc(view, n0...) does not (core/src/Kokkos_CopyViews.hpp:1580-1790)
+// (pairs are spelled std::pair<size_t, size_t>, not make_pair: nvcc prints the first spelling it saw of a type into the host
+// stubs of extended lambdas, and make_pair's spelling contains a GCC built-in trait that GCC then rejects in a signature)
+template <class D, class... P>
+void realloc(View<D, P...>& v, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0, size_t n6 = 0, size_t n7 = 0) {
+  using V = View<D, P...>;
+  static_assert(V::is_managed, "kb200::realloc: the View must own its allocation");
+  const size_t n[8] = {n0, n1, n2, n3, n4, n5, n6, n7};
+  bool same = v.is_allocated();
+  for (int r = 0; r < Impl::data_type_dynamic_rank<D>::value; ++r) same = same && v.extent(r) == n[r];
+  if (same) { deep_copy(v, typename V::non_const_value_type()); return; }
+  v = V(v.label(), n0, n1, n2, n3, n4, n5, n6, n7);
+}
+template <class D, class... P>
+void resize(View<D, P...>& v, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0, size_t n6 = 0, size_t n7 = 0) {
+  using V = View<D, P...>;
+  static_assert(V::is_managed, "kb200::resize: the View must own its allocation");
+  static_assert(V::rank >= 1 && V::rank <= 3, "kb200::resize: rank 1..3");
+  const size_t n[8] = {n0, n1, n2, n3, n4, n5, n6, n7};
+  bool same = true;
+  for (int r = 0; r < Impl::data_type_dynamic_rank<D>::value; ++r) same = same && v.extent(r) == n[r];
+  if (same) return;
+  V fresh(v.label(), n0, n1, n2, n3, n4, n5, n6, n7);
+  size_t c[3];
+  for (int r = 0; r < 3; ++r) c[r] = r < V::rank ? (v.extent(r) < fresh.extent(r) ? v.extent(r) : fresh.extent(r)) : 1;
+  if (c[0] * c[1] * c[2] > 0) {
+    if constexpr (V::rank == 1) deep_copy(subview(fresh, std::pair<size_t, size_t>(0, c[0])), subview(v, std::pair<size_t, size_t>(0, c[0])));
+    else if constexpr (V::rank == 2)
+      deep_copy(subview(fresh, std::pair<size_t, size_t>(0, c[0]), std::pair<size_t, size_t>(0, c[1])), subview(v, std::pair<size_t, size_t>(0, c[0]), std::pair<size_t, size_t>(0, c[1])));
+    else
+      deep_copy(subview(fresh, std::pair<size_t, size_t>(0, c[0]), std::pair<size_t, size_t>(0, c[1]), std::pair<size_t, size_t>(0, c[2])),
+                subview(v, std::pair<size_t, size_t>(0, c[0]), std::pair<size_t, size_t>(0, c[1]), std::pair<size_t, size_t>(0, c[2])));
+  }
+  v = fresh;
+}
+
 template <class D, class... P>
 typename View<D, P...>::HostMirror create_mirror_view(const View<D, P...>& v) {
   return typename View<D, P...>::HostMirror(view_alloc(WithoutInitializing, v.label() + "_mirror"), v.extent(0), v.extent(1), v.extent(2), v.extent(3), v.extent(4), v.extent(5), v.extent(6), v.extent(7));

@@ -719,4 +719,58 @@ int kb200_case_strided_subview(i64 n0, i64 n1, i64 n2, i64* out) {
   });
 }
 
+// ------------------------------------------------------------------ UniqueToken + resize / realloc
+int kb200_case_tokens_resize(i64 n, i64* out) {
+  return guarded([&] {
+    using Experimental::UniqueToken;
+    using Experimental::UniqueTokenScope;
+    UniqueToken<B200, UniqueTokenScope::Instance> tokens{B200()};
+    UniqueToken<B200, UniqueTokenScope::Instance> few(64, B200());
+    out[0] = tokens.size();
+    View<int*> inuse("inuse", (size_t)tokens.size()), inuse_few("inuse_few", 64);
+    View<i64*> hits("hits", (size_t)tokens.size());
+    View<i64> errors("errors");
+    parallel_for(RangePolicy<>(0, n), KB200_LAMBDA(const i64) {
+      Experimental::AcquireUniqueToken<B200, UniqueTokenScope::Instance> t(tokens);
+      const int id = t.value();
+      if (id < 0 || id >= tokens.size() || atomic_fetch_add(&inuse(id), 1) != 0) atomic_add(&errors(), (i64)1);
+      hits(id) += 1;  // exclusive while the token is held
+      if (atomic_fetch_add(&inuse(id), -1) != 1) atomic_add(&errors(), (i64)1);
+    });
+    // a caller-sized token set, used from one warp's worth of threads (never more holders than tokens)
+    parallel_for(RangePolicy<>(0, 32), KB200_LAMBDA(const i64) {
+      const int id = few.acquire();
+      if (id < 0 || id >= few.size() || atomic_fetch_add(&inuse_few(id), 1) != 0) atomic_add(&errors(), (i64)1);
+      if (atomic_fetch_add(&inuse_few(id), -1) != 1) atomic_add(&errors(), (i64)1);
+      few.release(id);
+    });
+    i64 e = -1, total = 0;
+    deep_copy(e, errors);
+    out[1] = e;
+    parallel_reduce(tokens.size(), KB200_LAMBDA(const i64 i, i64& u) { u += hits(i); }, total);
+    out[2] = total;
+    // resize keeps the common box, realloc does not
+    View<i64*> a("a", (size_t)n);
+    parallel_for(n, KB200_LAMBDA(const i64 i) { a(i) = i + 1; });
+    resize(a, (size_t)(2 * n));
+    i64 s1 = 0, s2 = 0;
+    parallel_reduce(2 * n, KB200_LAMBDA(const i64 i, i64& u) { u += a(i); }, s1);
+    out[3] = (i64)a.extent(0); out[4] = s1;
+    resize(a, (size_t)(n / 2));
+    parallel_reduce(n / 2, KB200_LAMBDA(const i64 i, i64& u) { u += a(i); }, s2);
+    out[5] = (i64)a.extent(0); out[6] = s2;
+    View<i64**> m("m", 5, 7);
+    parallel_for(MDRangePolicy<Rank<2>>({0, 0}, {5, 7}), KB200_LAMBDA(const i64 i, const i64 j) { m(i, j) = 10 * i + j; });
+    resize(m, 8, 4);
+    i64 s3 = 0;
+    parallel_reduce(MDRangePolicy<Rank<2>>({0, 0}, {8, 4}), KB200_LAMBDA(const i64 i, const i64 j, i64& u) { u += m(i, j); }, s3);
+    out[7] = (i64)m.extent(0) * 10 + (i64)m.extent(1); out[8] = s3;
+    realloc(m, 3, 3);
+    i64 s4 = -1;
+    parallel_reduce(MDRangePolicy<Rank<2>>({0, 0}, {3, 3}), KB200_LAMBDA(const i64 i, const i64 j, i64& u) { u += m(i, j); }, s4);
+    out[9] = s4;
+    return 0;
+  });
+}
+
 }  // extern "C"

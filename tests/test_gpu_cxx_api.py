@@ -283,3 +283,15 @@ def test_strided_subview_copy_fill(cases):
     assert out[4] == 0 and out[5] == 0
     assert out[6] == (n0 - 2) * n2 and out[7] == 0
     assert out[8] == sum(10 * i + 4 for i in range(6)) and out[9] == 9
+
+
+def test_unique_token_and_resize(cases):
+    """UniqueToken: every acquire() hands out an index nobody else holds, default- and caller-sized (TestUniqueToken.hpp:36-70); resize keeps the common index box, realloc zero-fills (Kokkos_CopyViews.hpp:1580-1790)."""
+    n = 200003
+    out = np.zeros(16, dtype=np.int64)
+    ok(cases, cases.kb200_case_tokens_resize(c_int64(n), P(out)))
+    assert out[0] == 2048 * 148 and out[1] == 0 and out[2] == n
+    assert out[3] == 2 * n and out[4] == n * (n + 1) // 2
+    h = n // 2
+    assert out[5] == h and out[6] == h * (h + 1) // 2
+    assert out[7] == 84 and out[8] == sum(10 * i + j for i in range(5) for j in range(4)) and out[9] == 0
