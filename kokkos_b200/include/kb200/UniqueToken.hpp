@@ -37,7 +37,9 @@ class UniqueToken {
     if constexpr (Scope == UniqueTokenScope::Global) m_locks = Impl2::global_token_locks(space);
     else m_locks = View<unsigned*>("kb200::UniqueToken::locks", (size_t)space.concurrency());
   }
-  // a caller-chosen number of tokens (Instance scope only, as in the reference)
+  // a caller-chosen number of tokens (Instance scope only, as in the reference).  As there, the caller must not let more
+  // threads hold or wait for tokens at once than there are tokens: a warp leaves acquire() together, so waiting lanes can
+  // keep their warp-mates' tokens from ever being released.
   template <UniqueTokenScope S = Scope, class = std::enable_if_t<S == UniqueTokenScope::Instance>>
   UniqueToken(size_type max_size, const execution_space& = execution_space()) : m_locks("kb200::UniqueToken::locks", (size_t)max_size) {}
 
