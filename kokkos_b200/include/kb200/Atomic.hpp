@@ -507,6 +507,9 @@ struct AtomicDataElement {
   KB200_FORCEINLINE_FUNCTION void operator&=(const value_type& v) const { atomic_and(ptr, v); }
   KB200_FORCEINLINE_FUNCTION void operator|=(const value_type& v) const { atomic_or(ptr, v); }
   KB200_FORCEINLINE_FUNCTION void operator^=(const value_type& v) const { atomic_xor(ptr, v); }
+  KB200_FORCEINLINE_FUNCTION void operator%=(const value_type& v) const { atomic_mod(ptr, v); }
+  KB200_FORCEINLINE_FUNCTION void operator<<=(const value_type& v) const { atomic_lshift(ptr, (unsigned)v); }
+  KB200_FORCEINLINE_FUNCTION void operator>>=(const value_type& v) const { atomic_rshift(ptr, (unsigned)v); }
   KB200_FORCEINLINE_FUNCTION value_type operator++() const { return atomic_fetch_add(ptr, value_type(1)) + value_type(1); }
   KB200_FORCEINLINE_FUNCTION value_type operator--() const { return atomic_fetch_sub(ptr, value_type(1)) - value_type(1); }
   KB200_FORCEINLINE_FUNCTION value_type operator++(int) const { return atomic_fetch_add(ptr, value_type(1)); }

@@ -165,6 +165,13 @@ class View : public Impl::ViewStrides<Impl::view_is_strided<Props...>::value> {
   static constexpr bool is_device = !std::is_same<memory_space, HostSpace>::value;
   static constexpr bool is_strided = std::is_same<array_layout, LayoutStride>::value;
   using HostMirror = View<std::remove_const_t<DataType>, array_layout, HostSpace>;
+  using host_mirror_space = HostSpace;
+  // bytes an allocation of these extents takes (core/src/Kokkos_View.hpp required_allocation_size)
+  static constexpr size_t required_allocation_size(size_t n0 = 0, size_t n1 = 0, size_t n2 = 0, size_t n3 = 0, size_t n4 = 0, size_t n5 = 0,
+                                                   size_t n6 = 0, size_t n7 = 0) {
+    return (rank > 0 ? n0 : 1) * (rank > 1 ? n1 : 1) * (rank > 2 ? n2 : 1) * (rank > 3 ? n3 : 1) * (rank > 4 ? n4 : 1) * (rank > 5 ? n5 : 1) *
+           (rank > 6 ? n6 : 1) * (rank > 7 ? n7 : 1) * sizeof(value_type);
+  }
   using traits = View;  // View::traits::memory_space, ::array_layout, ::value_type ... (the reference's ViewTraits members)
   using non_const_type = View<DataType, Props...>;
 
@@ -249,6 +256,22 @@ class View : public Impl::ViewStrides<Impl::view_is_strided<Props...>::value> {
       for (int r = 0; r < rank; ++r) off += ix[r] * this->m_stride[r];
     } else if constexpr (std::is_same<array_layout, LayoutLeft>::value) {
       for (int r = rank - 1; r >= 0; --r) off = off * m_ext[r] + ix[r];  // (constant trip count: unrolled)
+    } else {
+      for (int r = 0; r < rank; ++r) off = off * m_ext[r] + ix[r];
+    }
+    return ref(off);
+  }
+
+  // access(i0, ..., i7): element access that ignores the indices beyond the rank (core/src/Kokkos_View.hpp View::access)
+  template <class... Is>
+  KB200_FORCEINLINE_FUNCTION reference_type access(const Is... is) const {
+    static_assert(sizeof...(Is) >= (size_t)rank && sizeof...(Is) <= 8, "kb200::View::access: between rank and 8 indices");
+    const size_t ix[sizeof...(Is) > 0 ? sizeof...(Is) : 1] = {(size_t)is...};
+    size_t off = 0;
+    if constexpr (is_strided) {
+      for (int r = 0; r < rank; ++r) off += ix[r] * this->m_stride[r];
+    } else if constexpr (std::is_same<array_layout, LayoutLeft>::value) {
+      for (int r = rank - 1; r >= 0; --r) off = off * m_ext[r] + ix[r];
     } else {
       for (int r = 0; r < rank; ++r) off = off * m_ext[r] + ix[r];
     }
@@ -365,6 +388,25 @@ class View : public Impl::ViewStrides<Impl::view_is_strided<Props...>::value> {
   size_t m_ext[8];
   Impl::AllocRecord* m_rec;
 };
+
+// two Views are equal when they are the same window on the same memory (core/src/Kokkos_View.hpp operator==)
+template <class D1, class... P1, class D2, class... P2>
+KB200_INLINE_FUNCTION bool operator==(const View<D1, P1...>& a, const View<D2, P2...>& b) {
+  using A = View<D1, P1...>; using B = View<D2, P2...>;
+  if (!std::is_same<typename A::value_type, typename B::value_type>::value || !std::is_same<typename A::array_layout, typename B::array_layout>::value ||
+      !std::is_same<typename A::memory_space, typename B::memory_space>::value || (int)A::rank != (int)B::rank)
+    return false;
+  if ((const void*)a.data() != (const void*)b.data()) return false;
+  for (int r = 0; r < A::rank; ++r)
+    if (a.extent(r) != b.extent(r) || a.stride(r) != b.stride(r)) return false;
+  return true;
+}
+template <class D1, class... P1, class D2, class... P2>
+KB200_INLINE_FUNCTION bool operator!=(const View<D1, P1...>& a, const View<D2, P2...>& b) { return !(a == b); }
+
+// Kokkos::ViewTraits<DataType, Props...>: the analysed properties; here the View publishes them itself
+template <class DataType, class... Props>
+using ViewTraits = View<DataType, Props...>;
 
 template <class T> struct is_view : std::false_type {};
 template <class D, class... P> struct is_view<View<D, P...>> : std::true_type {};
