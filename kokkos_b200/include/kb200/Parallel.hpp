@@ -242,13 +242,19 @@ int array_reduce_launch(const RangePolicy<P...>& policy, const F& f, int count, 
   });
 }
 template <class T, class Tag, class F, class... P, int CAP>
-int array_reduce_launch(const MDRangePolicy<P...>& policy, const F& f, int count, T* rh, T* rd, std::integral_constant<int, CAP>) {
+int array_reduce_launch(const MDRangePolicy<P...>& policy_in, const F& f, int count, T* rh, T* rd, std::integral_constant<int, CAP>) {
   using Policy = MDRangePolicy<P...>;
   using Index = typename Policy::index_type;
+  Policy policy(policy_in);
   b200_instance* inst = policy.space().impl_instance();
   HostRuntime rt(inst);
-  MDLaunchShape<Policy> sh(policy);
   auto k = array_mdrange_reduce_kernel<F, Tag, T, CAP, Policy::rank, Index>;
+  for (;;) {  // per-thread accumulator arrays are register-hungry: shrink a default tile until the kernel fits
+    int fit = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, k, MDLaunchShape<Policy>(policy).threads, 0);
+    if (fit >= 1 || !policy.impl_shrink_default_tile()) break;
+  }
+  MDLaunchShape<Policy> sh(policy);
   int bps = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, sh.threads, 0);
   if (bps < 1) bps = 1;

@@ -343,6 +343,24 @@ class MDRangePolicy : public Impl::PolicyTraits<Props...> {
   static constexpr int max_tile_product = 1024;  // one tile = one thread block
   int max_total_tile_size() const { return Impl::get_tile_size_properties(m_space).max_total_tile_size; }
   bool impl_tune_tile_size() const { return m_tune_tile_size; }
+  // The launcher calls this when a kernel cannot run with the DEFAULT tile (a register-heavy functor: 512 threads leave 128
+  // registers each): halve the slowest dimension that is still wider than 1 and recount the tiles.  False when the tile was
+  // chosen by the caller or nothing is left to shrink.
+  bool impl_shrink_default_tile() {
+    if (!m_tune_tile_size) return false;
+    int d = rank - 1;
+    while (d >= 0 && m_tile[d] <= 1) --d;
+    if (d < 0) return false;
+    m_tile[d] = (m_tile[d] + 1) / 2;
+    m_num_tiles = 1; m_prod_tile_dims = 1;
+    for (int r = 0; r < rank; ++r) {
+      const index_type len = m_upper[r] - m_lower[r];
+      m_tile_end[r] = (len + m_tile[r] - 1) / m_tile[r];
+      m_num_tiles *= m_tile_end[r];
+      m_prod_tile_dims *= m_tile[r];
+    }
+    return true;
+  }
   // the tile the policy would pick on its own for these extents (KokkosExp_MDRangePolicy.hpp:335-352)
   tile_type tile_size_recommended() const {
     const Impl::TileSizeProperties pr = Impl::get_tile_size_properties(m_space);

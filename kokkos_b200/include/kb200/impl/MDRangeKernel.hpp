@@ -144,13 +144,22 @@ struct MDLaunchShape {
 
 template <class Policy, class F>
 struct MDRangeFor {
-  static int run(const Policy& pol, const F& f) {
-    if (pol.m_num_tiles <= 0) return 0;
+  static int run(const Policy& pol_in, const F& f) {
+    if (pol_in.m_num_tiles <= 0) return 0;
     constexpr int RANK = Policy::rank;
     using Index = typename Policy::index_type;
     using Tag = typename Policy::work_tag;
-    MDLaunchShape<Policy> sh(pol);
+    Policy pol(pol_in);
     HostRuntime rt(pol.space().impl_instance());
+    for (;;) {  // a default tile the kernel's register count does not allow is shrunk until it launches
+      MDLaunchShape<Policy> probe(pol);
+      probe.maybe_coarsen(rt.sm_count());
+      auto kp = probe.coarsen > 1 ? mdrange_for_kernel<F, Tag, RANK, Index, MDLaunchShape<Policy>::kCoarsen> : mdrange_for_kernel<F, Tag, RANK, Index, 1>;
+      int fit = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, kp, probe.threads, 0);
+      if (fit >= 1 || !pol.impl_shrink_default_tile()) break;
+    }
+    MDLaunchShape<Policy> sh(pol);
     sh.maybe_coarsen(rt.sm_count());
     auto k = sh.coarsen > 1 ? mdrange_for_kernel<F, Tag, RANK, Index, MDLaunchShape<Policy>::kCoarsen> : mdrange_for_kernel<F, Tag, RANK, Index, 1>;
     int bps = 0;
@@ -168,12 +177,21 @@ struct MDRangeFor {
 template <class Policy, class F, class Red>
 struct MDRangeReduce {
   using V = typename Red::value_type;
-  static int run(const Policy& pol, const F& f, const Red& red, V* result_host, V* result_dev) {
+  static int run(const Policy& pol_in, const F& f, const Red& red, V* result_host, V* result_dev) {
     constexpr int RANK = Policy::rank;
     using Index = typename Policy::index_type;
     using Tag = typename Policy::work_tag;
-    MDLaunchShape<Policy> sh(pol);
+    Policy pol(pol_in);
     HostRuntime rt(pol.space().impl_instance());
+    for (;;) {  // (as in MDRangeFor: shrink a default tile the kernel cannot launch with)
+      MDLaunchShape<Policy> probe(pol);
+      probe.maybe_coarsen(rt.sm_count());
+      auto kp = probe.coarsen > 1 ? mdrange_reduce_kernel<F, Tag, Red, RANK, Index, MDLaunchShape<Policy>::kCoarsen> : mdrange_reduce_kernel<F, Tag, Red, RANK, Index, 1>;
+      int fit = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, kp, probe.threads, 0);
+      if (fit >= 1 || !pol.impl_shrink_default_tile()) break;
+    }
+    MDLaunchShape<Policy> sh(pol);
     sh.maybe_coarsen(rt.sm_count());
     auto k = sh.coarsen > 1 ? mdrange_reduce_kernel<F, Tag, Red, RANK, Index, MDLaunchShape<Policy>::kCoarsen> : mdrange_reduce_kernel<F, Tag, Red, RANK, Index, 1>;
     int bps = 0;

@@ -773,4 +773,33 @@ int kb200_case_tokens_resize(i64 n, i64* out) {
   });
 }
 
+// ------------------------------------------------------------------ MDRange default tile vs a register-heavy functor
+// 72 live 64-bit values per thread: more than the 128 registers a 512-thread default tile leaves, so the launcher has to shrink
+// the tile (Policy::impl_shrink_default_tile) instead of failing with "too many resources requested".
+int kb200_case_mdrange_heavy(i64 n0, i64 n1, i64 n2, unsigned long long* hy) {
+  return guarded([&] {
+    using u64 = unsigned long long;
+    View<u64***> y("y", (size_t)n0, (size_t)n1, (size_t)n2);
+    parallel_for(MDRangePolicy<Rank<3>>({0, 0, 0}, {n0, n1, n2}), KB200_LAMBDA(const i64 i, const i64 j, const i64 k) {
+      u64 a[72];
+#pragma unroll
+      for (int t = 0; t < 72; ++t) a[t] = (u64)(i + 3 * j + 7 * k) * (u64)(t + 1) + 0x9E3779B97F4A7C15ull;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int t = 0; t < 72; ++t) a[t] = a[t] * a[(t + 7) % 72] + (u64)(r + 1);
+      }
+      u64 s = 0;
+#pragma unroll
+      for (int t = 0; t < 72; ++t) s ^= a[t] + (u64)t;
+      y(i, j, k) = s;
+    });
+    auto h = create_mirror_view_and_copy(HostSpace(), y);
+    for (i64 k = 0; k < n2; ++k)
+      for (i64 j = 0; j < n1; ++j)
+        for (i64 i = 0; i < n0; ++i) hy[(k * n1 + j) * n0 + i] = h(i, j, k);
+    return 0;
+  });
+}
+
 }  // extern "C"
