@@ -37,6 +37,13 @@ def env_int(name, default):
         return default
 
 
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return max(1, os.cpu_count() or 1)
+
+
 class ClockSampler:
     """nvidia-smi sampler for the timed region (B200_PROFILING.md 'clocks' line)."""
 
@@ -94,7 +101,11 @@ def cpu_reference_leg(log2n, reps):
     from oracle.bindings import Ref, Port, ref_available
     n = 1 << log2n
     if ref_available():
-        ref = Ref(0)  # all host threads
+        # every host core this process may run on, stated explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers and
+        # the OpenMP runtime would inherit it (round-1 SCALE runs measured a 1-thread reference at N > 1)
+        cores = host_cores()
+        os.environ["OMP_NUM_THREADS"] = str(cores)
+        ref = Ref(cores)
         t_red, s = ref.time_reduce_sum_f64(n, reps)
         t_scan, total = ref.time_scan_excl_i64(n, reps)
         kind, cores = "reference", ref.threads

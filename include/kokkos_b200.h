@@ -98,6 +98,10 @@ int b200_scratch_get(b200_instance* inst, int kind, size_t bytes, void** dev_ptr
  * counter_base is always 0 and kept for ABI stability */
 int b200_scan_begin(b200_instance* inst, uint64_t ntiles, uint64_t* epoch, uint64_t* counter_base,
                     unsigned long long** counter_dev);
+/* start a chunk-synchronous scan launch (kb200/impl/ScanChunked.hpp): first LL step tag of the launch, the instance's
+ * descriptor ring (16 rows x 256 CTAs x 16 bytes, zero-initialised once) and a pinned error word (device address) */
+int b200_chunk_begin(b200_instance* inst, uint64_t nsteps, unsigned* tag_base, unsigned long long** desc_dev, unsigned** err_dev);
+unsigned b200_chunk_error(b200_instance* inst);
 /* one call for everything a reduction launch needs: partials (>= partial_bytes), the ticket word,
  * and (if want_result_slot) a fresh pinned+mapped result slot of >= value_bytes from a 64-entry ring */
 int b200_reduce_scratch(b200_instance* inst, size_t partial_bytes, size_t value_bytes, int want_result_slot,
@@ -193,6 +197,43 @@ int b200_spmv_crs_f64(b200_instance*, int64_t nrows, const int64_t* row_map, con
  *      Host buffers should be pinned (b200_malloc_host_pinned).  Blocking. ---- */
 int b200_reduce_sum_f64_host(b200_instance*, const double* host_x, int64_t n, double* result);
 int b200_scan_excl_i64_host(b200_instance*, const int64_t* host_x, int64_t* host_y, int64_t n, int64_t seed, int64_t* total);
+
+/* ---- one-box communicator (SURVEY.md 8b last row, 8e): one process per GPU, peer-mapped mailboxes over NVLink/NVSwitch
+ *      and our own kernels -- no NCCL, no torch.  The reference has no collectives: a Kokkos program holds one Kokkos::Cuda
+ *      instance per device (core/src/Cuda/Kokkos_Cuda_Instance.cpp:268-283, core/unit_test/TestMultiGPU.hpp) and combines
+ *      the per-device results on the host.  Every call is stream-ordered on the instance's stream and must be made by all
+ *      ranks in the same order (like MPI/NCCL collectives).  Payloads are at most 1024 bytes per rank. ---- */
+typedef struct b200_comm b200_comm;
+int b200_comm_unique_id(char* out, size_t capacity);           /* rank 0 makes it, hands it to the others (>= 40 bytes) */
+int b200_comm_init(b200_instance* inst, int rank, int world, const char* unique_id, b200_comm** out); /* collective, blocking */
+int b200_comm_finalize(b200_comm* comm);                       /* collective, blocking */
+int b200_comm_rank(b200_comm* comm);
+int b200_comm_world(b200_comm* comm);
+int b200_comm_barrier(b200_comm* comm);                        /* device-side, stream ordered */
+int b200_comm_host_barrier(b200_comm* comm);                   /* host-side (processes) */
+unsigned b200_comm_error(b200_comm* comm);                     /* non-zero after a device-side time-out: 0xA.. all-gather, 0xD.. scan mailbox */
+int b200_allgather_bytes(b200_comm* comm, const void* src_dev, void* dst_dev, size_t bytes_per_rank); /* dst: world * bytes, rank order */
+/* in-place folds of `count` values per rank, evaluated in RANK ORDER on every rank (bitwise identical everywhere) */
+int b200_allreduce_sum_f64(b200_comm* comm, double* buf_dev, int count);
+int b200_allreduce_min_f64(b200_comm* comm, double* buf_dev, int count);
+int b200_allreduce_max_f64(b200_comm* comm, double* buf_dev, int count);
+int b200_allreduce_sum_i64(b200_comm* comm, int64_t* buf_dev, int count);
+int b200_allreduce_min_i64(b200_comm* comm, int64_t* buf_dev, int count);
+int b200_allreduce_max_i64(b200_comm* comm, int64_t* buf_dev, int count);
+/* MinLoc / MaxLoc / MinMaxLoc joins (core/src/Kokkos_Parallel_Reduce.hpp:441-449,501-509,628-644); equal extrema keep the
+ * lowest location, which is what the OpenMP reference yields with its thread-ordered joins */
+int b200_allreduce_minloc_f64(b200_comm* comm, b200_valloc_f64* buf_dev);
+int b200_allreduce_maxloc_f64(b200_comm* comm, b200_valloc_f64* buf_dev);
+int b200_allreduce_minmaxloc_f64(b200_comm* comm, b200_minmaxloc_f64* buf_dev);
+/* Block-cyclic distributed parallel_scan, ONE fused kernel per GPU, 16 B/element at any world size
+ * (kb200/impl/ScanChunked.hpp): global block c (block_elems elements) lives on rank c % world as local block c / world;
+ * x/y point at the rank's local blocks stored back to back.  b200_comm_cyclic_layout reports the block size, this rank's
+ * local length and the number of lock-step rounds for a global length.  total = sum over ALL ranks' elements.
+ * Replaces ParallelScanWithTotal<...,Cuda> (Kokkos_Cuda_Parallel_Range.hpp:704-1047) + the user's cross-device fix-up. */
+int b200_comm_cyclic_layout(b200_comm* comm, int elem_bytes, int64_t n_global, int64_t* block_elems, int64_t* n_local, int64_t* nsteps);
+int b200_comm_scan_excl_i64(b200_comm* comm, const int64_t* x_local, int64_t* y_local, int64_t n_global, int64_t* total_host, int64_t* total_dev);
+int b200_comm_scan_incl_i64(b200_comm* comm, const int64_t* x_local, int64_t* y_local, int64_t n_global, int64_t* total_host, int64_t* total_dev);
+int b200_comm_scan_excl_f64(b200_comm* comm, const double* x_local, double* y_local, int64_t n_global, double* total_host, double* total_dev);
 
 /* ---- tuning knobs (benchmark harness only; defaults are the shipped configuration) ---- */
 int b200_tune_set(const char* key, int value);

@@ -98,7 +98,23 @@ def load_library() -> ctypes.CDLL:
         "b200_result_wait": [P, P, c_uint64, c_char_p],
         "b200_reduce_sum_f64_host": [P, P, c_int64, P],
         "b200_scan_excl_i64_host": [P, P, P, c_int64, c_int64, P],
+        "b200_comm_unique_id": [ctypes.c_char_p, c_size_t],
+        "b200_comm_init": [P, c_int, c_int, c_char_p, POINTER(P)],
+        "b200_comm_finalize": [P],
+        "b200_comm_barrier": [P],
+        "b200_comm_host_barrier": [P],
+        "b200_allgather_bytes": [P, P, P, c_size_t],
+        "b200_allreduce_minloc_f64": [P, P],
+        "b200_allreduce_maxloc_f64": [P, P],
+        "b200_allreduce_minmaxloc_f64": [P, P],
+        "b200_comm_cyclic_layout": [P, c_int, c_int64, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)],
+        "b200_comm_scan_excl_i64": [P, P, P, c_int64, P, P],
+        "b200_comm_scan_incl_i64": [P, P, P, c_int64, P, P],
+        "b200_comm_scan_excl_f64": [P, P, P, c_int64, P, P],
     }
+    for op in ("sum", "min", "max"):
+        for sfx in ("f64", "i64"):
+            sig[f"b200_allreduce_{op}_{sfx}"] = [P, P, c_int]
     for name in ("sum_f64", "sum_f32", "sum_i64", "sum_i32", "min_f64", "max_f64", "min_i64", "max_i64", "min_i32",
                  "max_i32", "minmax_f64"):
         sig[f"b200_reduce_{name}"] = [P, P, c_int64, P, P]
@@ -119,6 +135,11 @@ def load_library() -> ctypes.CDLL:
     lib.b200_instance_id.restype = c_uint32
     lib.b200_instance_sm_count.argtypes = [P]
     lib.b200_instance_sm_count.restype = c_int
+    for name in ("b200_comm_rank", "b200_comm_world"):
+        getattr(lib, name).argtypes = [P]
+        getattr(lib, name).restype = c_int
+    lib.b200_comm_error.argtypes = [P]
+    lib.b200_comm_error.restype = c_uint32
     _lib = lib
     return lib
 
@@ -354,6 +375,68 @@ class B200:
             self.finalize()
         except Exception:
             pass
+
+
+def comm_unique_id() -> str:
+    """Rank 0 creates the id and hands it to the other ranks out of band (the role of ncclGetUniqueId)."""
+    buf = ctypes.create_string_buffer(64)
+    _check(load_library().b200_comm_unique_id(buf, 64))
+    return buf.value.decode()
+
+
+class Comm:
+    """One-box communicator: one process per GPU, peer-mapped mailboxes over NVLink, the library's own kernels
+    (``b200_comm_*`` / ``b200_allreduce_*`` / ``b200_comm_scan_*`` in include/kokkos_b200.h).  Every method is a
+    collective: all ranks call it, in the same order, on their instance's stream."""
+
+    def __init__(self, space: B200, rank: int, world: int, unique_id: str = ""):
+        self.space = space
+        self.lib = space.lib
+        h = c_void_p()
+        _check(self.lib.b200_comm_init(space.handle, rank, world, unique_id.encode(), byref(h)))
+        self.handle = h
+        self.rank, self.world = rank, world
+
+    def barrier(self) -> None:
+        _check(self.lib.b200_comm_barrier(self.handle))
+
+    def host_barrier(self) -> None:
+        _check(self.lib.b200_comm_host_barrier(self.handle))
+
+    def error(self) -> int:
+        return int(self.lib.b200_comm_error(self.handle))
+
+    def allgather(self, src_dev: int, dst_dev: int, bytes_per_rank: int) -> None:
+        _check(self.lib.b200_allgather_bytes(self.handle, src_dev, dst_dev, bytes_per_rank))
+
+    def allreduce(self, op: str, buf_dev: int, count: int, dtype) -> None:
+        """In-place fold (sum/min/max) of `count` f64 or i64 values per rank, in rank order."""
+        _check(getattr(self.lib, f"b200_allreduce_{op}_{_SUFFIX[np.dtype(dtype)]}")(self.handle, buf_dev, count))
+
+    def allreduce_loc(self, kind: str, buf_dev: int) -> None:
+        """kind: minloc / maxloc (b200_valloc_f64) or minmaxloc (b200_minmaxloc_f64), in place."""
+        _check(getattr(self.lib, f"b200_allreduce_{kind}_f64")(self.handle, buf_dev))
+
+    def cyclic_layout(self, n_global: int, dtype) -> tuple[int, int, int]:
+        """(block_elems, n_local, nsteps) of the block-cyclic distribution the fused scan works on."""
+        b, nl, ns = c_int64(), c_int64(), c_int64()
+        _check(self.lib.b200_comm_cyclic_layout(self.handle, np.dtype(dtype).itemsize, n_global, byref(b), byref(nl), byref(ns)))
+        return b.value, nl.value, ns.value
+
+    def parallel_scan(self, x: View, y: View, n_global: int, inclusive: bool = False, total_dev: int = 0, blocking: bool = True):
+        """Distributed parallel_scan over a block-cyclic View (local blocks in x / y); returns the GLOBAL total if blocking."""
+        sfx = _SUFFIX[x.dtype]
+        name = f"b200_comm_scan_{'incl' if inclusive else 'excl'}_{sfx}"
+        if not hasattr(self.lib, name):
+            raise B200Error(-3, f"{name} is not provided")
+        out = _CT[sfx]()
+        _check(getattr(self.lib, name)(self.handle, x.ptr, y.ptr, n_global, byref(out) if blocking else None, total_dev or None))
+        return out.value if blocking else None
+
+    def finalize(self) -> None:
+        if self.handle:
+            _check(self.lib.b200_comm_finalize(self.handle))
+            self.handle = None
 
 
 def version() -> str:

@@ -153,6 +153,8 @@ int b200_finalize(b200_instance* I) {
   if (I->tile_counter) cudaFree(I->tile_counter);
   if (I->scan_status) cudaFree(I->scan_status);
   if (I->scan_values) cudaFree(I->scan_values);
+  if (I->chunk_desc) cudaFree(I->chunk_desc);
+  if (I->chunk_err) cudaFreeHost(I->chunk_err);
   if (I->functor_spill) cudaFree(I->functor_spill);
   if (I->team_l1) cudaFree(I->team_l1);
   if (I->owns_stream && I->stream) cudaStreamDestroy(I->stream);
@@ -370,6 +372,29 @@ int b200_scan_begin(b200_instance* I, uint64_t ntiles, uint64_t* epoch, uint64_t
   *counter_dev = I->tile_counter;
   return 0;
 }
+
+int b200_chunk_begin(b200_instance* I, uint64_t nsteps, unsigned* tag_base, unsigned long long** desc_dev, unsigned** err_dev) {
+  if (!I) return b200_set_error(B200_ENOTINIT, "b200_chunk_begin", nullptr);
+  if (!tag_base || !desc_dev || !err_dev) return b200_set_error(B200_EINVAL, "b200_chunk_begin", "NULL out pointer");
+  std::lock_guard<std::mutex> lock(I->mutex);
+  if (!I->chunk_desc) {  // first use: 64 KiB of LL descriptors (zero = tag 0 = never valid) + one pinned error word
+    constexpr size_t kBytes = 16 * 256 * 16;
+    CU_TRY(cudaSetDevice(I->device), "b200_chunk_begin");
+    CU_TRY(cudaMalloc((void**)&I->chunk_desc, kBytes), "b200_chunk_begin");
+    CU_TRY(cudaMemsetAsync(I->chunk_desc, 0, kBytes, I->stream), "b200_chunk_begin");
+    CU_TRY(cudaHostAlloc((void**)&I->chunk_err, 64, cudaHostAllocMapped), "b200_chunk_begin");
+    I->chunk_err[0] = 0;
+    CU_TRY(cudaHostGetDevicePointer((void**)&I->chunk_err_dev, I->chunk_err, 0), "b200_chunk_begin");
+  }
+  *tag_base = I->chunk_tag;
+  I->chunk_tag += (uint32_t)nsteps;  // tags only ever grow (mod 2^32): a ring entry is rewritten every 16 steps, so no stale tag can match
+  if (I->chunk_tag == 0) I->chunk_tag = 1;
+  *desc_dev = I->chunk_desc;
+  *err_dev = I->chunk_err_dev;
+  return 0;
+}
+
+unsigned b200_chunk_error(b200_instance* I) { return (I && I->chunk_err) ? I->chunk_err[0] : 0u; }
 
 int b200_launch(b200_instance* I, const void* func, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by,
                 unsigned bz, size_t smem, void** args) {

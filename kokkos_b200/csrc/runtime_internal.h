@@ -41,6 +41,12 @@ struct b200_instance {
   void* scan_values = nullptr;
   size_t scan_values_bytes = 0;
 
+  // chunk-synchronous scan (impl/ScanChunked.hpp): LL descriptor ring, step-tag counter, pinned error word
+  unsigned long long* chunk_desc = nullptr;
+  uint32_t chunk_tag = 1;
+  unsigned* chunk_err = nullptr;      // pinned host
+  unsigned* chunk_err_dev = nullptr;  // same word, device address
+
   void* functor_spill = nullptr;
   size_t functor_spill_bytes = 0;
   void* team_l1 = nullptr;

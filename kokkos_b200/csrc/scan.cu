@@ -5,6 +5,7 @@
 #include <kokkos_b200.h>
 #include "runtime_internal.h"
 #include <kb200/impl/ScanContig.hpp>
+#include <kb200/impl/ScanChunked.hpp>
 
 using namespace kb200;
 using kb200::Impl::ContigScanLaunch;
@@ -20,7 +21,16 @@ int scan_entry(b200_instance* I, const char* where, const T* x, T* y, int64_t n,
   // the warp-specialised kernel needs both Views 16-byte aligned (bulk copies); otherwise the uniform kernel
   const bool aligned = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0);
   const int ws = aligned ? b200_tune("scan.ws", 2) : 0;
+  #ifdef B200_SWEEP
   const int sleep_ns = b200_tune("scan.sleep", 0), dbg = b200_tune("scan.dbg", 0);
+#else
+  const int sleep_ns = 0, dbg = 0;  // the experiment switches (skip look-back / skip scan) exist in sweep builds only
+#endif
+  if (aligned && b200_tune("scan.chunked", 0)) {  // chunk-synchronous kernel (the multi-GPU scan at world 1)
+    using L = kb200::Impl::ChunkScanLaunch<T, 384, 9, 4, 4, INCL>;
+    const int grid = L::max_grid(I->device, I->props.sm_count);
+    if (grid > 0) return L::run(I, nullptr, grid, L::steps_for(n, grid), x, y, n, seed, seed_dev, nseeds, th, td);
+  }
 #define CFG(BL, NV, NB, LB) \
   if (!ws && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 0>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg, nseeds);
 #define ZCFG(BL, NV, NB, LB) \
@@ -32,9 +42,9 @@ int scan_entry(b200_instance* I, const char* where, const T* x, T* y, int64_t n,
 #define WCFG(BL, NV, NB, LB) \
   if (ws == 1 && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 1>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg, nseeds);
   XCFG(128, 9, 4, 1)   // shipped: 5 variants x ~90 configurations measured, profiles/r01_scan_probe_v*.log
-  WCFG(256, 9, 2, 2)
   if (!ws) return ContigScanLaunch<T, 256, 9, 2, 2, INCL, 0>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg, nseeds);
 #ifdef B200_SWEEP
+  WCFG(256, 9, 2, 2)
   if constexpr (sizeof(T) == 8 && !INCL) {
     CFG(256, 9, 2, 1) CFG(256, 9, 2, 4) CFG(256, 9, 3, 2) CFG(256, 9, 3, 4)
     CFG(256, 7, 2, 2) CFG(256, 7, 3, 2) CFG(256, 7, 3, 4) CFG(256, 11, 2, 2) CFG(256, 11, 2, 4)
@@ -101,6 +111,9 @@ int b200_scan_excl_i64_seeds_dev(b200_instance* I, const int64_t* x, int64_t* y,
 }  // extern "C"
 
 #ifdef B200_SWEEP
+extern "C" int b200_debug_chunk_stats(unsigned long long* out32) {
+  return (int)cudaMemcpy(out32, kb200::Impl::chunk_stats_buffer(), 32 * 8, cudaMemcpyDeviceToHost);
+}
 // diagnostics for tools/scan_probe.py (sweep build only; not declared in the public header)
 extern "C" int b200_debug_scan_stats(unsigned long long* out16, int reset) {
   if (out16) cudaMemcpyFromSymbol(out16, kb200::Impl::g_scan_stats, 16 * sizeof(unsigned long long));

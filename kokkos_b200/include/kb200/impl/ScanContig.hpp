@@ -18,6 +18,9 @@
 #ifndef KB200_IMPL_SCANCONTIG_HPP
 #define KB200_IMPL_SCANCONTIG_HPP
 
+#include "LL.hpp"
+#include <type_traits>
+
 #include "Collectives.hpp"
 #include "HostRuntime.hpp"
 #include "Ptx.hpp"
@@ -30,11 +33,12 @@ namespace Impl {
 // [3] cycles inside look-back [4] compute-warp cycles waiting for the prefix [5] compute-warp cycles waiting for data
 // [6] tiles (compute) [7] cycles the look-back warp waits for its own aggregate
 __device__ unsigned long long g_scan_stats[16];
+__device__ unsigned long long g_round_ts[4][8192];  // per round: [0] first tile landed [1] last tile landed [2] round aggregate sent [3] base published
 // accumulated in registers, flushed once per warp at exit: per-event global atomics perturb the kernel badly
 struct ScanStats {
-  unsigned long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long v[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // [8] cycles resolving the round base (non-leaders) [9] same, leaders [10] leaders [11] late bases
   KB200_DEVICE_FUNCTION void flush() {
-    for (int i = 0; i < 8; ++i) if (v[i]) atomicAdd(&g_scan_stats[i], v[i]);
+    for (int i = 0; i < 12; ++i) if (v[i]) atomicAdd(&g_scan_stats[i], v[i]);
   }
 };
 #define KB200_STATS_DECL ScanStats kb_stats
@@ -74,7 +78,20 @@ struct ScanContigParams {
   int bulk_load, bulk_store;  // 16-byte alignment of x / y allows the TMA path
   int spin_sleep_ns;          // back-off between polls of an unpublished predecessor (0 = none)
   int dbg_flags;              // tools/sweep.py experiments only: 1 = skip look-back, 2 = skip the scan (pure copy)
+  // ---- multi-GPU "rounds" (block-cyclic distributed scan; csrc/comm.cu).  tpr == 0: single GPU, nothing below is used.
+  int64 tpr;                  // tiles per round; a round (tpr * TILE elements) is the block of the block-cyclic distribution
+  int rank, world;
+  unsigned rtag_base;         // LL tag of round k = rtag_base + k (never 0), identical on all ranks
+  unsigned long long* rdesc;  // this GPU: [kRoundRing][4] LL words {base(k), running_before(k)}, written by the round leader
+  unsigned long long* mbox;   // this GPU: [kRoundRing][kRoundMaxWorld][2] LL words: round aggregates of every rank
+  unsigned long long* peer_mbox[8];  // the same array on every rank (peer-mapped over NVLink)
+  unsigned long long* racc;   // this GPU: [kRoundRing][2] round accumulators (integral T): Sum(lo32) | count<<48, Sum(hi32) | count<<48
+  unsigned* err;              // pinned host word, set before a time-out trap
+  unsigned long long timeout_ns;
 };
+constexpr int kRoundRing = 64;      // rows of the round descriptor / mailbox rings: live rounds (<= 2 + grid*NSTAGE/tpr) + look-back reach
+constexpr int kRoundLookback = 16;  // how many rounds back a round leader looks for a published running total
+constexpr int kRoundMaxWorld = 8;
 
 template <class T>
 KB200_DEVICE_FUNCTION T scan_seed(const ScanContigParams<T>& p) {
@@ -93,19 +110,6 @@ KB200_DEVICE_FUNCTION void scan_counter_release(unsigned long long* counter) {
     counter[1] = 0ull;
     __threadfence();
   }
-}
-
-template <class T>
-KB200_DEVICE_FUNCTION unsigned long long to_bits(T v) {
-  unsigned long long b = 0;
-  memcpy(&b, &v, sizeof(T));
-  return b;
-}
-template <class T>
-KB200_DEVICE_FUNCTION T from_bits(unsigned long long b) {
-  T v;
-  memcpy(&v, &b, sizeof(T));
-  return v;
 }
 
 template <class T>
@@ -136,7 +140,7 @@ KB200_DEVICE_FUNCTION void ld_desc(const ScanDesc16* d, unsigned long long& a, u
 }
 
 template <class T, int LBW>
-KB200_DEVICE_FUNCTION T lookback_sum(const ScanDesc16* desc, int64 tile, unsigned long long epoch, int lane, int sleep_ns, int weak KB200_STATS_ARG) {
+KB200_DEVICE_FUNCTION T lookback_sum(const ScanDesc16* desc, int64 tile, unsigned long long epoch, int lane, int sleep_ns, int weak KB200_STATS_ARG, int64 lo = 0) {
   T excl = T(0);
   int64 wbase = tile - 1;
 #ifdef B200_SWEEP
@@ -148,11 +152,11 @@ KB200_DEVICE_FUNCTION T lookback_sum(const ScanDesc16* desc, int64 tile, unsigne
 #pragma unroll
     for (int j = 0; j < LBW; ++j) {
       const int64 idx = wbase - ((int64)j * 32 + lane);
-      if (idx >= 0) {
+      if (idx >= lo) {
         ld_desc(desc + idx, pay[j], st[j], weak);
       } else {
         pay[j] = 0;
-        st[j] = (epoch << 2) | kDescIncl;  // before the first tile: inclusive prefix = identity
+        st[j] = (epoch << 2) | kDescIncl;  // before the first tile (of the round): inclusive prefix = identity
       }
     }
     bool retry = false, done = false;
@@ -328,18 +332,6 @@ __global__ void __launch_bounds__(BLOCK) contig_scan_kernel(const ScanContigPara
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Warp-specialised variant (the shipped one for 16-byte aligned Views).
-//
-// The kernel above keeps every latency on the CTA's critical path: the tile-id atomic's round trip,
-// the wait for the previous bulk store to drain, the TMA issue and the look-back all happen between
-// barriers that the 8 compute warps sit in (first B200 sweep: 2.99 TB/s, profiles/r01_sweep_v1.log).
-// Here one extra warp is the DMA engine driver: it takes tile ids, issues the bulk loads NSTAGE
-// tiles ahead, and issues the bulk stores when the compute warps hand a finished stage back; all
-// hand-offs are mbarriers (full[s]: data landed; outready[s]: results are in smem).  The compute
-// warps only ever wait for (a) a tile that was requested NSTAGE tiles ago and (b) the look-back.
-// The look-back window is 32*LBW descriptors per step, wide enough that the distance to the nearest
-// resolved predecessor (~ tile arrival rate x resolution latency) fits in one or two steps.
 KB200_DEVICE_FUNCTION void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 KB200_DEVICE_FUNCTION void mbar_arrive(void* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
@@ -353,169 +345,94 @@ KB200_DEVICE_FUNCTION void bulk_wait_read_dyn(int k) {
   }
 }
 
-template <class T, int CBLOCK, int NV, int NSTAGE, int LBW, bool INCLUSIVE>
-__global__ void __launch_bounds__(CBLOCK + 32) contig_scan_ws_kernel(const ScanContigParams<T> p) {
-  static_assert(NV % 2 == 1, "odd vector count keeps blocked smem accesses conflict free");
-  constexpr int ITEMS = NV * 16 / (int)sizeof(T);
-  constexpr int EPV = 16 / (int)sizeof(T);
-  constexpr int TILE = CBLOCK * ITEMS;
-  constexpr unsigned TILE_BYTES = TILE * sizeof(T);
-  constexpr int NWARPS = CBLOCK / 32;
+// single-producer request ring (shared memory) from a service warp to the CTA's round warp; called by ONE lane
+template <int RQ>
+KB200_DEVICE_FUNCTION void rq_push(int64& nreq, unsigned long long* rq_full, unsigned long long* rq_empty, int64* s_rq, int64 kk) {
+  const int slot = (int)(nreq % RQ);
+  if (nreq >= RQ) ptx::mbar_wait(&rq_empty[slot], (unsigned)(((nreq / RQ) - 1) & 1));
+  s_rq[slot] = kk;
+  ptx::mbar_arrive(&rq_full[slot]);
+  ++nreq;
+}
 
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  T* const bufs = reinterpret_cast<T*>(smem_raw);
-  __shared__ __align__(8) unsigned long long full[NSTAGE];
-  __shared__ __align__(8) unsigned long long outready[NSTAGE];
-  __shared__ int64 s_tile_id[NSTAGE];
-  __shared__ T s_warp[32];
-  __shared__ T s_tile_prefix;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  KB200_STATS_DECL;
-  if (tid == 0) {
-#pragma unroll
-    for (int b = 0; b < NSTAGE; ++b) { ptx::mbar_init(&full[b], 1); ptx::mbar_init(&outready[b], 1); }
-    ptx::fence_mbar_init();
-  }
-  __syncthreads();
-
-  if (warp == NWARPS) {
-    // ================= DMA warp =================
-    int64 jl = 0, js = 0, nvalid = 0;
-    int64 tl[NSTAGE];  // tile id held by each stage
-    bool more = true;
-    while (more || js < nvalid) {
-      if (more && jl - js < NSTAGE) {
-        const int st = (int)(jl % NSTAGE);
-        if (jl >= NSTAGE && lane == 0) bulk_wait_read_dyn<NSTAGE - 1>((int)(js - 1 - (jl - NSTAGE)));
-        long long tile = 0;
-        if (lane == 0) tile = (long long)(atomicAdd(p.counter, 1ull) - p.counter_base);
-        tile = __shfl_sync(kFullMask, tile, 0);
-        if (lane == 0) s_tile_id[st] = tile;
-#pragma unroll
-        for (int b = 0; b < NSTAGE; ++b) if (b == st) tl[b] = tile;
-        if (tile >= p.ntiles) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full[st]);  // wake the consumers on the end-of-work marker
-          more = false;
-        } else {
-          const int64 base = tile * TILE;
-          T* const buf = bufs + (size_t)st * TILE;
-          if (p.bulk_load && base + TILE <= p.n) {
-            if (lane == 0) {
-              ptx::mbar_expect_tx(&full[st], TILE_BYTES);
-              ptx::bulk_g2s(buf, p.x + base, TILE_BYTES, &full[st]);
-            }
-          } else {
-            const int64 remaining = p.n - base;
-            for (int i = lane; i < TILE; i += 32) buf[i] = (i < remaining) ? p.x[base + i] : T(0);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[st]);
-          }
-          ++nvalid;
+// Round k of a block-cyclic distributed scan (ROUNDS kernels):
+//   prefix of a tile = base(k) + (prefix inside the round),
+//   base(k) = running_before(k) + aggregates of round k on the ranks below this one,
+//   running_before(k) = total of rounds < k over ALL ranks.
+// round_publish (warp-collective, run by the CTA's ROUND warp) computes base(kk) and publishes it in this GPU's round
+// descriptor; it is requested by the look-back warp that finished the LAST tile of round kk-1 (or tile 0 for kk = 0), so
+// it starts the moment this GPU's aggregate of round kk-1 exists and never queues behind parked tiles.  kk == nrounds
+// writes the global total instead.  running_before comes from a round-level look-back: the nearest earlier round whose
+// running_before is published plus the aggregates (all ranks) from there on -- publishers never wait for each other in
+// a chain (a chain costs several L2 round trips per round: measured 4.6 us/round against a 1.5 us round time).
+template <class T>
+KB200_DEVICE_FUNCTION void round_publish(const ScanContigParams<T>& p, int64 kk, int64 nrounds, int lane, bool have_own, T own_prev) {
+  T rb = T(0);
+  if (kk > 0) {
+    int m = 0;
+    T rbm = T(0);
+    {
+      unsigned long long t0 = 0;
+      for (unsigned spin = 0;; ++spin) {
+        const int64 k2 = kk - 1 - lane;
+        bool have = false;
+        T v = T(0);
+        if (k2 >= 0 && lane < kRoundLookback) {
+          unsigned long long w0, w1;
+          ll::ld_gpu(p.rdesc + (size_t)(k2 % kRoundRing) * 4 + 2, w0, w1);
+          have = ll::ok(w0, w1, p.rtag_base + (unsigned)k2);
+          v = ll::unpack<T>(w0, w1);
         }
-        ++jl;
-      }
-      if (js < nvalid) {
-        const int st = (int)(js % NSTAGE);
-        if (ptx::mbar_try_wait(&outready[st], (unsigned)((js / NSTAGE) & 1))) {
-          long long tile = 0;
-#pragma unroll
-          for (int b = 0; b < NSTAGE; ++b) if (b == st) tile = tl[b];
-          const int64 base = tile * TILE;
-          T* const buf = bufs + (size_t)st * TILE;
-          if (p.bulk_store && base + TILE <= p.n) {
-            if (lane == 0) ptx::bulk_s2g(p.y + base, buf, TILE_BYTES);
-          } else {
-            const int64 remaining = p.n - base;
-            for (int i = lane; i < TILE && i < remaining; i += 32) p.y[base + i] = buf[i];
-            __syncwarp();
-          }
-          if (lane == 0) ptx::bulk_commit();  // one group per stage hand-back keeps the drain accounting uniform
-          ++js;
+        const unsigned bal = __ballot_sync(kFullMask, have);
+        if (bal) {
+          m = __ffs(bal) - 1;
+          rbm = shfl_idx(v, m);
+          break;
+        }
+        if ((spin & 1023u) == 1023u) {
+          const unsigned long long t = ll::now_ns();
+          if (t0 == 0) t0 = t;
+          else if (t - t0 > p.timeout_ns) ll::give_up(p.err, 0xD2000000u);
         }
       }
     }
+    T part = T(0);
+    const int cnt = (m + 1) * p.world;
+    for (int e = lane; e < cnt; e += 32) {
+      const int64 k2 = kk - 1 - e / p.world;
+      if (have_own && e / p.world == 0 && e % p.world == p.rank) { part += own_prev; continue; }  // just collected by this warp
+      part += ll::wait_value<T, true>(p.mbox + ((size_t)(k2 % kRoundRing) * kRoundMaxWorld + (e % p.world)) * 2, p.rtag_base + (unsigned)k2,
+                                      p.timeout_ns, p.err, 0xD1000000u | (unsigned)(e % p.world));
+    }
+    __syncwarp();
+    rb = rbm + warp_sum_all<T>(part);
+  }
+  if (kk == nrounds) {  // past the last round: running_before is the global total
     if (lane == 0) {
-      ptx::bulk_wait_read<0>();
-      scan_counter_release(p.counter);
+      if (p.total0) *p.total0 = rb;
+      if (p.total1) *p.total1 = rb;
     }
-    { KB200_STATS_FLUSH(); return; }
+    return;
   }
-
-  // ================= compute warps =================
-  const T seed = scan_seed(p);
-  for (int64 j = 0;; ++j) {
-    const int st = (int)(j % NSTAGE);
-    ptx::mbar_wait(&full[st], (unsigned)((j / NSTAGE) & 1));
-    const int64 cur = s_tile_id[st];
-    if (cur >= p.ntiles) break;
-    T* const buf = bufs + (size_t)st * TILE;
-    if (p.dbg_flags & 2) {  // experiment: hand the stage straight back (measures the bulk-copy pipeline alone)
-      ptx::fence_proxy_async_smem();
-      named_bar_sync(1, CBLOCK);
-      if (tid == 0) mbar_arrive(&outready[st]);
-      continue;
-    }
-    T v[ITEMS];
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(buf + (size_t)tid * ITEMS);
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        const uint4 q = src[k];
-        memcpy(&v[k * EPV], &q, 16);
-      }
-    }
-    T tsum = T(0);
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) tsum += v[k];
-    const T tincl = warp_incl_scan(tsum, lane);
-    if (lane == 31) s_warp[warp] = tincl;
-    named_bar_sync(1, CBLOCK);
-    if (warp == 0) {
-      const T w = lane < NWARPS ? s_warp[lane] : T(0);
-      const T wi = warp_incl_scan(w, lane);
-      if (lane < NWARPS) s_warp[lane] = wi - w;
-      const T agg = shfl_idx(wi, NWARPS - 1);
-      ScanDesc16* const d = p.desc + cur;
-      T excl = T(0);
-      if (cur == 0) {
-        if (lane == 0) ptx::st_relaxed_v2(d, to_bits(agg), (p.epoch << 2) | kDescIncl);
-      } else {
-        if (lane == 0) ptx::st_relaxed_v2(d, to_bits(agg), (p.epoch << 2) | kDescAgg);
-        if (!(p.dbg_flags & 1)) excl = lookback_sum<T, LBW>(p.desc, cur, p.epoch, lane, p.spin_sleep_ns, p.dbg_flags & 8 KB200_STATS_PASS);
-        if (lane == 0) ptx::st_relaxed_v2(d, to_bits((T)(excl + agg)), (p.epoch << 2) | kDescIncl);
-      }
-      if (lane == 0) {
-        s_tile_prefix = excl;
-        if (cur == p.ntiles - 1) {
-          const T total = excl + agg;
-          if (p.total0) *p.total0 = total;
-          if (p.total1) *p.total1 = total;
-        }
-      }
-    }
-    named_bar_sync(1, CBLOCK);
-    T run = seed + s_tile_prefix + s_warp[warp] + (tincl - tsum);
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-      const T in = v[k];
-      if (INCLUSIVE) { run += in; v[k] = run; } else { v[k] = run; run += in; }
-    }
-    {
-      uint4* dst = reinterpret_cast<uint4*>(buf + (size_t)tid * ITEMS);
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        uint4 q;
-        memcpy(&q, &v[k * EPV], 16);
-        dst[k] = q;
-      }
-    }
-    ptx::fence_proxy_async_smem();
-    named_bar_sync(1, CBLOCK);
-    if (tid == 0) mbar_arrive(&outready[st]);
+  const int row = (int)(kk % kRoundRing);
+  const unsigned tag = p.rtag_base + (unsigned)kk;
+  if (lane == 0) {  // running_before first: later publishers may already build on it while this one waits for the lower ranks
+    unsigned long long w0, w1;
+    ll::pack(rb, tag, w0, w1);
+    ll::st_gpu(p.rdesc + (size_t)row * 4 + 2, w0, w1);
   }
-  KB200_STATS_FLUSH();
+  T v = T(0);
+  if (lane < p.rank) v = ll::wait_value<T, true>(p.mbox + (size_t)row * kRoundMaxWorld * 2 + 2 * lane, tag, p.timeout_ns, p.err, 0xD3000000u | (unsigned)lane);
+  __syncwarp();
+  const T before = warp_sum_all<T>(v);
+  if (lane == 0) {
+    unsigned long long w0, w1;
+    ll::pack((T)(rb + before), tag, w0, w1);
+    ll::st_gpu(p.rdesc + (size_t)row * 4, w0, w1);
+#ifdef B200_SWEEP
+    if (kk < 8192) g_round_ts[3][kk] = ll::now_ns();
+#endif
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -531,8 +448,8 @@ __global__ void __launch_bounds__(CBLOCK + 32) contig_scan_ws_kernel(const ScanC
 //   AGGREGATE warp: full[s] -> sum the stage (lane-strided LDS.128) -> publish AGGREGATE -> aggready[s]
 //   LOOK-BACK warp: aggready[s] -> look-back -> publish INCLUSIVE -> prefix[s] -> prefready[s]
 //   compute warps : full[s] -> blocked scan in registers -> prefready[s] -> add prefix -> smem -> outready[s]
-template <class T, int CBLOCK, int NV, int NSTAGE, int LBW, bool INCLUSIVE>
-__global__ void __launch_bounds__(CBLOCK + 96) contig_scan_ws2_kernel(const ScanContigParams<T> p) {
+template <class T, int CBLOCK, int NV, int NSTAGE, int LBW, bool INCLUSIVE, bool ROUNDS = false>
+__global__ void __launch_bounds__(CBLOCK + 96 + (ROUNDS ? 32 : 0)) contig_scan_ws2_kernel(const ScanContigParams<T> p) {
   static_assert(NV % 2 == 1, "odd vector count keeps blocked smem accesses conflict free");
   constexpr int ITEMS = NV * 16 / (int)sizeof(T);
   constexpr int EPV = 16 / (int)sizeof(T);
@@ -547,6 +464,14 @@ __global__ void __launch_bounds__(CBLOCK + 96) contig_scan_ws2_kernel(const Scan
   __shared__ T s_agg[NSTAGE];
   __shared__ T s_prefix[NSTAGE];
   __shared__ T s_warp[32];
+  __shared__ T s_base;  // ROUNDS: base of the round of the tile the compute warps are working on
+  constexpr int RQ = 8;  // ROUNDS: requests "publish base(kk)" from a service warp to the round warp
+  // integral T: tiles ADD their aggregate to a per-round accumulator (two fire-and-forget reds, no ordering needed: each
+  // word carries its own arrival count), so the round aggregate exists ~1 us after the last tile landed instead of after
+  // the last tile's look-back (measured 4.9 us).  Floating point keeps the look-back value (fixed summation order).
+  constexpr bool ATOMIC_AGG = ROUNDS && std::is_integral<T>::value;
+  __shared__ __align__(8) unsigned long long rq_full[RQ], rq_empty[RQ];
+  __shared__ int64 s_rq[RQ];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   KB200_STATS_DECL;
@@ -556,9 +481,60 @@ __global__ void __launch_bounds__(CBLOCK + 96) contig_scan_ws2_kernel(const Scan
       ptx::mbar_init(&full[b], 1); ptx::mbar_init(&aggready[b], 1);
       ptx::mbar_init(&prefready[b], 1); ptx::mbar_init(&outready[b], 1);
     }
+    if constexpr (ROUNDS) {
+#pragma unroll
+      for (int b = 0; b < RQ; ++b) { ptx::mbar_init(&rq_full[b], 1); ptx::mbar_init(&rq_empty[b], 1); }
+    }
     ptx::fence_mbar_init();
   }
   __syncthreads();
+
+  if constexpr (ROUNDS) {
+    if (warp == NWARPS + 3) {
+      // ================= ROUND warp: publishes round bases on request (see round_publish) =================
+      const int64 nrounds = p.ntiles / p.tpr;
+      for (int64 c = 0;; ++c) {
+        const int slot = (int)(c % RQ);
+        ptx::mbar_wait(&rq_full[slot], (unsigned)((c / RQ) & 1));
+        const int64 kk = s_rq[slot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rq_empty[slot]);
+        if (kk < 0) return;
+        T own_prev = T(0);
+        if constexpr (ATOMIC_AGG) {
+          if (kk > 0) {  // collect this GPU's aggregate of round kk-1 from the accumulator, re-arm it, send it to every rank
+            const int64 k1 = kk - 1;
+            unsigned long long* const acc = p.racc + (size_t)(k1 % kRoundRing) * 2;
+            unsigned long long w0 = 0, w1 = 0;
+            if (lane == 0) {
+              unsigned long long t0 = 0;
+              for (unsigned spin = 0;; ++spin) {
+                ll::ld_gpu(acc, w0, w1);
+                if ((w0 >> 48) == (unsigned long long)p.tpr && (w1 >> 48) == (unsigned long long)p.tpr) break;
+                if ((spin & 1023u) == 1023u) {
+                  const unsigned long long t = ll::now_ns();
+                  if (t0 == 0) t0 = t;
+                  else if (t - t0 > p.timeout_ns) ll::give_up(p.err, 0xD7000000u);
+                }
+              }
+              ll::st_gpu(acc, 0ull, 0ull);
+            }
+            const unsigned long long bits = (w0 & 0xffffffffffffull) + ((w1 & 0xffffffffffffull) << 32);
+            own_prev = shfl_idx(from_bits<T>(bits), 0);
+            if (lane < p.world) {
+              unsigned long long a0, a1;
+              ll::pack(own_prev, p.rtag_base + (unsigned)k1, a0, a1);
+              ll::st_sys(p.peer_mbox[lane] + (size_t)(k1 % kRoundRing) * kRoundMaxWorld * 2 + 2 * p.rank, a0, a1);
+            }
+#ifdef B200_SWEEP
+            if (lane == 0 && k1 < 8192) g_round_ts[2][k1] = ll::now_ns();
+#endif
+          }
+        }
+        round_publish<T>(p, kk, nrounds, lane, ATOMIC_AGG && kk > 0, own_prev);
+      }
+    }
+  }
 
   if (warp == NWARPS) {
     // ================= DMA warp =================
@@ -626,12 +602,16 @@ __global__ void __launch_bounds__(CBLOCK + 96) contig_scan_ws2_kernel(const Scan
 
   if (warp == NWARPS + 1) {
     // ================= AGGREGATE warp =================
+    int64 agg_nreq = 0;  // ATOMIC_AGG: requests handed to the round warp so far (lane 0)
     for (int64 j = 0;; ++j) {
       const int st = (int)(j % NSTAGE);
       ptx::mbar_wait(&full[st], (unsigned)((j / NSTAGE) & 1));
       const int64 cur = s_tile_id[st];
       if (cur >= p.ntiles) {
-        if (lane == 0) mbar_arrive(&aggready[st]);  // pass the end-of-work marker on
+        if (lane == 0) {
+          mbar_arrive(&aggready[st]);  // pass the end-of-work marker on
+          if constexpr (ATOMIC_AGG) rq_push<RQ>(agg_nreq, rq_full, rq_empty, s_rq, -1);
+        }
         { KB200_STATS_FLUSH(); return; }
       }
       const uint4* src = reinterpret_cast<const uint4*>(bufs + (size_t)st * TILE);
@@ -647,15 +627,36 @@ __global__ void __launch_bounds__(CBLOCK + 96) contig_scan_ws2_kernel(const Scan
       }
       const T agg = warp_sum_all<T>((acc[0] + acc[1]) + (acc[2] + acc[3]));
       if (lane == 0) {
-        ptx::st_relaxed_v2(p.desc + cur, to_bits(agg), (p.epoch << 2) | (cur == 0 ? kDescIncl : kDescAgg));
+        const bool first = ROUNDS ? (cur % p.tpr == 0) : (cur == 0);  // nothing before it (in its round): the aggregate IS the inclusive prefix
+#ifdef B200_SWEEP
+        if constexpr (ROUNDS) {
+          const int64 kq = cur / p.tpr;
+          if (kq < 8192 && cur % p.tpr == 0) g_round_ts[0][kq] = ll::now_ns();
+          if (kq < 8192 && cur % p.tpr == p.tpr - 1) g_round_ts[1][kq] = ll::now_ns();
+        }
+#endif
+        ptx::st_relaxed_v2(p.desc + cur, to_bits(agg), (p.epoch << 2) | (first ? kDescIncl : kDescAgg));
         s_agg[st] = agg;
         mbar_arrive(&aggready[st]);
+        if constexpr (ATOMIC_AGG) {
+          const int64 kq = cur / p.tpr;
+          unsigned long long* const acc = p.racc + (size_t)(kq % kRoundRing) * 2;
+          const unsigned long long b = to_bits(agg);
+          asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc), "l"((b & 0xffffffffull) | (1ull << 48)) : "memory");
+          asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(acc + 1), "l"((b >> 32) | (1ull << 48)) : "memory");
+          if (cur == 0) rq_push<RQ>(agg_nreq, rq_full, rq_empty, s_rq, 0);
+          if (cur % p.tpr == p.tpr - 1) rq_push<RQ>(agg_nreq, rq_full, rq_empty, s_rq, kq + 1);  // the round's last tile has landed
+        }
       }
     }
   }
 
   if (warp == NWARPS + 2) {
     // ================= LOOK-BACK warp =================
+    int64 nreq = 0;  // ROUNDS without ATOMIC_AGG: requests handed to the round warp so far (lane 0)
+    auto request_round = [&](int64 kk) {
+      if (lane == 0) rq_push<RQ>(nreq, rq_full, rq_empty, s_rq, kk);
+    };
     for (int64 j = 0;; ++j) {
       const int st = (int)(j % NSTAGE);
 #ifdef B200_SWEEP
@@ -666,16 +667,33 @@ __global__ void __launch_bounds__(CBLOCK + 96) contig_scan_ws2_kernel(const Scan
       if (lane == 0) KB200_STAT_ADD(7, clock64() - t_w2);
 #endif
       const int64 cur = s_tile_id[st];
-      if (cur >= p.ntiles) return;
+      if (cur >= p.ntiles) {
+        if constexpr (ROUNDS && !ATOMIC_AGG) request_round(-1);  // no more work for the round warp
+        return;
+      }
       const T agg = s_agg[st];
       T excl = T(0);
-      if (cur > 0) {
-        if (!(p.dbg_flags & 1)) excl = lookback_sum<T, LBW>(p.desc, cur, p.epoch, lane, p.spin_sleep_ns, p.dbg_flags & 8 KB200_STATS_PASS);
+      const int64 lo = ROUNDS ? (cur / p.tpr) * p.tpr : 0;  // the look-back never leaves the tile's round
+      if (cur > lo) {
+        if (!(p.dbg_flags & 1)) excl = lookback_sum<T, LBW>(p.desc, cur, p.epoch, lane, p.spin_sleep_ns, p.dbg_flags & 8 KB200_STATS_PASS, lo);
         if (lane == 0) ptx::st_relaxed_v2(p.desc + cur, to_bits((T)(excl + agg)), (p.epoch << 2) | kDescIncl);
       }
+      if constexpr (ROUNDS && !ATOMIC_AGG) {
+        // the last tile of a round owns the round aggregate: store it into every rank's mailbox (NVLink), own rank included
+        if (cur - lo == p.tpr - 1 && lane < p.world) {
+          unsigned long long w0, w1;
+          ll::pack((T)(excl + agg), p.rtag_base + (unsigned)(cur / p.tpr), w0, w1);
+          ll::st_sys(p.peer_mbox[lane] + (size_t)((cur / p.tpr) % kRoundRing) * kRoundMaxWorld * 2 + 2 * p.rank, w0, w1);
+#ifdef B200_SWEEP
+          if (lane == 0 && cur / p.tpr < 8192) g_round_ts[2][cur / p.tpr] = ll::now_ns();
+#endif
+        }
+        if (cur == 0) request_round(0);
+        if (cur - lo == p.tpr - 1) request_round(cur / p.tpr + 1);  // this GPU's part of round k is known: the base of round k+1 can be built
+      }
       if (lane == 0) {
         s_prefix[st] = excl;
-        if (cur == p.ntiles - 1) {
+        if (!ROUNDS && cur == p.ntiles - 1) {
           const T total = excl + agg;
           if (p.total0) *p.total0 = total;
           if (p.total1) *p.total1 = total;
@@ -699,6 +717,11 @@ __global__ void __launch_bounds__(CBLOCK + 96) contig_scan_ws2_kernel(const Scan
 #endif
     const int64 cur = s_tile_id[st];
     if (cur >= p.ntiles) break;
+    unsigned long long rd0 = 0, rd1 = 0;
+    if constexpr (ROUNDS) {
+      // the round's base is usually published long before this tile needs it: request it now, look at it after the local work
+      if (tid == 0) ll::ld_gpu(p.rdesc + (size_t)((cur / p.tpr) % kRoundRing) * 4, rd0, rd1);
+    }
     T* const buf = bufs + (size_t)st * TILE;
     T v[ITEMS];
     {
@@ -714,6 +737,22 @@ __global__ void __launch_bounds__(CBLOCK + 96) contig_scan_ws2_kernel(const Scan
     for (int k = 0; k < ITEMS; ++k) tsum += v[k];
     const T tincl = warp_incl_scan(tsum, lane);
     if (lane == 31) s_warp[warp] = tincl;
+    if constexpr (ROUNDS) {
+      // the tile parks HERE until its round's base is published (not in the look-back warp: that one keeps publishing
+      // inclusive prefixes and round aggregates for the CTA's later tiles meanwhile)
+      if (tid == 0) {
+#ifdef B200_SWEEP
+        const long long t_rb = clock64();
+#endif
+        const unsigned rtag = p.rtag_base + (unsigned)(cur / p.tpr);
+        s_base = ll::ok(rd0, rd1, rtag) ? ll::unpack<T>(rd0, rd1)
+                                        : ll::wait_value<T, false>(p.rdesc + (size_t)((cur / p.tpr) % kRoundRing) * 4, rtag, p.timeout_ns, p.err, 0xD4000000u);
+#ifdef B200_SWEEP
+        KB200_STAT_ADD(8, clock64() - t_rb);
+        if (!ll::ok(rd0, rd1, rtag)) KB200_STAT_ADD(11, 1);
+#endif
+      }
+    }
     named_bar_sync(1, CBLOCK);
     T woff = T(0);  // exclusive offset of this warp inside the tile: every warp folds the <=32 warp totals itself
     {
@@ -729,6 +768,7 @@ __global__ void __launch_bounds__(CBLOCK + 96) contig_scan_ws2_kernel(const Scan
     if (tid == 0) KB200_STAT_ADD(4, clock64() - t_w1);
 #endif
     T run = seed + s_prefix[st] + woff + (tincl - tsum);
+    if constexpr (ROUNDS) run += s_base;
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
       const T in = v[k];
@@ -744,460 +784,32 @@ __global__ void __launch_bounds__(CBLOCK + 96) contig_scan_ws2_kernel(const Scan
       }
     }
     ptx::fence_proxy_async_smem();
-    named_bar_sync(1, CBLOCK);  // also orders the s_warp reads above before the next tile's writes
+    named_bar_sync(1, CBLOCK);  // also orders the s_warp / s_base reads above before the next tile's writes
     if (tid == 0) mbar_arrive(&outready[st]);
   }
   KB200_STATS_FLUSH();
 }
 
-// ---------------------------------------------------------------------------------------------
-// ws3 = ws2 with the DMA driver split in two warps.  Measured (profiles/r01_scan_probe_v3.log): one DMA thread
-// per CTA serialises tile-id atomic round trip -> wait for the previous store to drain -> issue, ~1.5 us per
-// tile, which caps a CTA at ~24 GB/s; configurations with one CTA per SM collapsed to 3 TB/s.  Here the LOAD warp
-// keeps one tile-id atomic in flight ahead of its use and only waits for a free stage; the STORE warp issues
-// the bulk store, waits for ITS reads, and recycles the stage (empty[s]).
-template <class T, int CBLOCK, int NV, int NSTAGE, int LBW, bool INCLUSIVE>
-__global__ void __launch_bounds__(CBLOCK + 128) contig_scan_ws3_kernel(const ScanContigParams<T> p) {
-  static_assert(NV % 2 == 1, "odd vector count keeps blocked smem accesses conflict free");
-  constexpr int ITEMS = NV * 16 / (int)sizeof(T);
-  constexpr int EPV = 16 / (int)sizeof(T);
-  constexpr int TILE = CBLOCK * ITEMS;
-  constexpr unsigned TILE_BYTES = TILE * sizeof(T);
-  constexpr int NWARPS = CBLOCK / 32;
-
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  T* const bufs = reinterpret_cast<T*>(smem_raw);
-  __shared__ __align__(8) unsigned long long full[NSTAGE], aggready[NSTAGE], prefready[NSTAGE], outready[NSTAGE], empty[NSTAGE];
-  __shared__ int64 s_tile_id[NSTAGE];
-  __shared__ T s_agg[NSTAGE];
-  __shared__ T s_prefix[NSTAGE];
-  __shared__ T s_warp[32];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  KB200_STATS_DECL;
-  if (tid == 0) {
-#pragma unroll
-    for (int b = 0; b < NSTAGE; ++b) {
-      ptx::mbar_init(&full[b], 1); ptx::mbar_init(&aggready[b], 1);
-      ptx::mbar_init(&prefready[b], 1); ptx::mbar_init(&outready[b], 1); ptx::mbar_init(&empty[b], 1);
-    }
-    ptx::fence_mbar_init();
-  }
-  __syncthreads();
-
-  if (warp == NWARPS) {
-    // ================= LOAD warp: tile ids (one atomic ahead) + bulk loads =================
-    long long next_tile = 0;
-    if (lane == 0) next_tile = (long long)(atomicAdd(p.counter, 1ull) - p.counter_base);
-    for (int64 jl = 0;; ++jl) {
-      const int st = (int)(jl % NSTAGE);
-      if (jl >= NSTAGE) ptx::mbar_wait(&empty[st], (unsigned)(((jl / NSTAGE) - 1) & 1));  // freed by the STORE warp
-      const long long tile = __shfl_sync(kFullMask, next_tile, 0);
-      if (lane == 0) s_tile_id[st] = tile;
-      if (tile >= p.ntiles) {
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&full[st]); scan_counter_release(p.counter); }
-        { KB200_STATS_FLUSH(); return; }
-      }
-      if (lane == 0) next_tile = (long long)(atomicAdd(p.counter, 1ull) - p.counter_base);  // round trip overlaps the load
-      const int64 base = tile * TILE;
-      T* const buf = bufs + (size_t)st * TILE;
-      if (p.bulk_load && base + TILE <= p.n) {
-        if (lane == 0) {
-          ptx::mbar_expect_tx(&full[st], TILE_BYTES);
-          ptx::bulk_g2s(buf, p.x + base, TILE_BYTES, &full[st]);
-        }
-      } else {
-        const int64 remaining = p.n - base;
-        for (int i = lane; i < TILE; i += 32) buf[i] = (i < remaining) ? p.x[base + i] : T(0);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[st]);
-      }
-    }
-  }
-
-  if (warp == NWARPS + 3) {
-    // ================= STORE warp: bulk stores + stage recycling =================
-    for (int64 js = 0;; ++js) {
-      const int st = (int)(js % NSTAGE);
-      const unsigned par = (unsigned)((js / NSTAGE) & 1);
-      ptx::mbar_wait(&full[st], par);
-      const int64 tile = s_tile_id[st];
-      if (tile >= p.ntiles) {
-        if (lane == 0) ptx::bulk_wait<0>();
-        { KB200_STATS_FLUSH(); return; }
-      }
-      ptx::mbar_wait(&outready[st], par);
-      const int64 base = tile * TILE;
-      T* const buf = bufs + (size_t)st * TILE;
-      if (p.bulk_store && base + TILE <= p.n) {
-        if (lane == 0) {
-          ptx::bulk_s2g(p.y + base, buf, TILE_BYTES);
-          ptx::bulk_commit();
-          ptx::bulk_wait_read<0>();  // the stage may be overwritten once its bytes have been read
-        }
-      } else {
-        const int64 remaining = p.n - base;
-        for (int i = lane; i < TILE && i < remaining; i += 32) p.y[base + i] = buf[i];
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[st]);
-    }
-  }
-
-  if (warp == NWARPS + 1) {
-    // ================= AGGREGATE warp =================
-    for (int64 j = 0;; ++j) {
-      const int st = (int)(j % NSTAGE);
-      ptx::mbar_wait(&full[st], (unsigned)((j / NSTAGE) & 1));
-      const int64 cur = s_tile_id[st];
-      if (cur >= p.ntiles) {
-        if (lane == 0) mbar_arrive(&aggready[st]);  // pass the end-of-work marker on
-        { KB200_STATS_FLUSH(); return; }
-      }
-      const uint4* src = reinterpret_cast<const uint4*>(bufs + (size_t)st * TILE);
-      T acc[4] = {T(0), T(0), T(0), T(0)};
-      constexpr int NVEC = (int)(TILE_BYTES / 16);
-#pragma unroll 4
-      for (int i = lane; i < NVEC; i += 32) {
-        const uint4 q = src[i];
-        T e[EPV];
-        memcpy(e, &q, 16);
-#pragma unroll
-        for (int k = 0; k < EPV; ++k) acc[k & 3] += e[k];
-      }
-      const T agg = warp_sum_all<T>((acc[0] + acc[1]) + (acc[2] + acc[3]));
-      if (lane == 0) {
-        ptx::st_relaxed_v2(p.desc + cur, to_bits(agg), (p.epoch << 2) | (cur == 0 ? kDescIncl : kDescAgg));
-        s_agg[st] = agg;
-        mbar_arrive(&aggready[st]);
-      }
-    }
-  }
-
-  if (warp == NWARPS + 2) {
-    // ================= LOOK-BACK warp =================
-    for (int64 j = 0;; ++j) {
-      const int st = (int)(j % NSTAGE);
+}  // namespace Impl
+}  // namespace kb200
 #ifdef B200_SWEEP
-      const long long t_w2 = clock64();
+#include "ScanContigSweep.hpp"
 #endif
-      ptx::mbar_wait(&aggready[st], (unsigned)((j / NSTAGE) & 1));
-#ifdef B200_SWEEP
-      if (lane == 0) KB200_STAT_ADD(7, clock64() - t_w2);
-#endif
-      const int64 cur = s_tile_id[st];
-      if (cur >= p.ntiles) return;
-      const T agg = s_agg[st];
-      T excl = T(0);
-      if (cur > 0) {
-        if (!(p.dbg_flags & 1)) excl = lookback_sum<T, LBW>(p.desc, cur, p.epoch, lane, p.spin_sleep_ns, p.dbg_flags & 8 KB200_STATS_PASS);
-        if (lane == 0) ptx::st_relaxed_v2(p.desc + cur, to_bits((T)(excl + agg)), (p.epoch << 2) | kDescIncl);
-      }
-      if (lane == 0) {
-        s_prefix[st] = excl;
-        if (cur == p.ntiles - 1) {
-          const T total = excl + agg;
-          if (p.total0) *p.total0 = total;
-          if (p.total1) *p.total1 = total;
-        }
-        mbar_arrive(&prefready[st]);
-      }
-    }
-  }
+namespace kb200 {
+namespace Impl {
 
-  // ================= compute warps =================
-  const T seed = scan_seed(p);
-  for (int64 j = 0;; ++j) {
-    const int st = (int)(j % NSTAGE);
-    const unsigned par = (unsigned)((j / NSTAGE) & 1);
-#ifdef B200_SWEEP
-    const long long t_w0 = clock64();
-#endif
-    ptx::mbar_wait(&full[st], par);
-#ifdef B200_SWEEP
-    if (tid == 0) { KB200_STAT_ADD(5, clock64() - t_w0); KB200_STAT_ADD(6, 1); }
-#endif
-    const int64 cur = s_tile_id[st];
-    if (cur >= p.ntiles) break;
-    T* const buf = bufs + (size_t)st * TILE;
-    T v[ITEMS];
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(buf + (size_t)tid * ITEMS);
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        const uint4 q = src[k];
-        memcpy(&v[k * EPV], &q, 16);
-      }
-    }
-    T tsum = T(0);
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) tsum += v[k];
-    const T tincl = warp_incl_scan(tsum, lane);
-    if (lane == 31) s_warp[warp] = tincl;
-    named_bar_sync(1, CBLOCK);
-    T woff = T(0);  // exclusive offset of this warp inside the tile: every warp folds the <=32 warp totals itself
-    {
-      const T w = lane < NWARPS ? s_warp[lane] : T(0);
-      const T wi = warp_incl_scan(w, lane);
-      woff = shfl_idx((T)(wi - w), warp);
-    }
-#ifdef B200_SWEEP
-    const long long t_w1 = clock64();
-#endif
-    ptx::mbar_wait(&prefready[st], par);
-#ifdef B200_SWEEP
-    if (tid == 0) KB200_STAT_ADD(4, clock64() - t_w1);
-#endif
-    T run = seed + s_prefix[st] + woff + (tincl - tsum);
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-      const T in = v[k];
-      if (INCLUSIVE) { run += in; v[k] = run; } else { v[k] = run; run += in; }
-    }
-    {
-      uint4* dst = reinterpret_cast<uint4*>(buf + (size_t)tid * ITEMS);
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        uint4 q;
-        memcpy(&q, &v[k * EPV], 16);
-        dst[k] = q;
-      }
-    }
-    ptx::fence_proxy_async_smem();
-    named_bar_sync(1, CBLOCK);  // also orders the s_warp reads above before the next tile's writes
-    if (tid == 0) mbar_arrive(&outready[st]);
-  }
-  KB200_STATS_FLUSH();
-}
+// what a launch of the block-cyclic distributed scan needs from the communicator (csrc/comm.cu)
+struct RoundPeers {
+  int rank = 0, world = 1;
+  unsigned long long* racc = nullptr;   // this GPU, [kRoundRing][2], zero between launches
+  unsigned long long* rdesc = nullptr;  // this GPU, [kRoundRing][4]
+  unsigned long long* mbox = nullptr;   // this GPU, [kRoundRing][kRoundMaxWorld][2]
+  unsigned long long* peer_mbox[kRoundMaxWorld] = {};
+  unsigned rtag_base = 1;
+  unsigned* err = nullptr;
+};
 
-// ---------------------------------------------------------------------------------------------
-// ws4 = ws3 with one LOOK-BACK warp per stage that starts when the tile id is taken, not when the tile's own
-// aggregate exists.  Measured (profiles/r01_scan_probe_v5_instrumented.log): one descriptor window costs ~1.3 us
-// under full HBM load and a tile needs ~2.3 windows, so a single look-back warp resolved one tile per ~3.5 us and
-// the compute warps waited 1.2-3 us per tile for the prefix.  Now the walk overlaps the load of the same tile and
-// the walks of the CTA's other stages.
-template <class T, int CBLOCK, int NV, int NSTAGE, int LBW, bool INCLUSIVE>
-__global__ void __launch_bounds__(CBLOCK + 96 + 32 * NSTAGE) contig_scan_ws4_kernel(const ScanContigParams<T> p) {
-  static_assert(NV % 2 == 1, "odd vector count keeps blocked smem accesses conflict free");
-  constexpr int ITEMS = NV * 16 / (int)sizeof(T);
-  constexpr int EPV = 16 / (int)sizeof(T);
-  constexpr int TILE = CBLOCK * ITEMS;
-  constexpr unsigned TILE_BYTES = TILE * sizeof(T);
-  constexpr int NWARPS = CBLOCK / 32;
-
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  T* const bufs = reinterpret_cast<T*>(smem_raw);
-  __shared__ __align__(8) unsigned long long full[NSTAGE], aggready[NSTAGE], prefready[NSTAGE], outready[NSTAGE], empty[NSTAGE], idready[NSTAGE];
-  __shared__ int64 s_tile_id[NSTAGE];
-  __shared__ T s_agg[NSTAGE];
-  __shared__ T s_prefix[NSTAGE];
-  __shared__ T s_warp[32];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  KB200_STATS_DECL;
-  if (tid == 0) {
-#pragma unroll
-    for (int b = 0; b < NSTAGE; ++b) {
-      ptx::mbar_init(&full[b], 1); ptx::mbar_init(&aggready[b], 1);
-      ptx::mbar_init(&prefready[b], 1); ptx::mbar_init(&outready[b], 1); ptx::mbar_init(&empty[b], 1); ptx::mbar_init(&idready[b], 1);
-    }
-    ptx::fence_mbar_init();
-  }
-  __syncthreads();
-
-  if (warp == NWARPS) {
-    // ================= LOAD warp: tile ids (one atomic ahead) + bulk loads =================
-    long long next_tile = 0;
-    int n_end = 0;
-    if (lane == 0) next_tile = (long long)(atomicAdd(p.counter, 1ull) - p.counter_base);
-    for (int64 jl = 0;; ++jl) {
-      const int st = (int)(jl % NSTAGE);
-      if (jl >= NSTAGE) ptx::mbar_wait(&empty[st], (unsigned)(((jl / NSTAGE) - 1) & 1));  // freed by the STORE warp
-      const long long tile = __shfl_sync(kFullMask, next_tile, 0);
-      if (lane == 0) { s_tile_id[st] = tile; mbar_arrive(&idready[st]); }  // the look-back may start now
-      if (tile >= p.ntiles) {
-        // end of work: every stage gets the marker once (each per-stage look-back warp must see it), no more ids are taken
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&full[st]); if (n_end == 0) scan_counter_release(p.counter); }
-        if (++n_end == NSTAGE) { KB200_STATS_FLUSH(); return; }
-        continue;
-      }
-      if (lane == 0) next_tile = (long long)(atomicAdd(p.counter, 1ull) - p.counter_base);  // round trip overlaps the load
-      const int64 base = tile * TILE;
-      T* const buf = bufs + (size_t)st * TILE;
-      if (p.bulk_load && base + TILE <= p.n) {
-        if (lane == 0) {
-          ptx::mbar_expect_tx(&full[st], TILE_BYTES);
-          ptx::bulk_g2s(buf, p.x + base, TILE_BYTES, &full[st]);
-        }
-      } else {
-        const int64 remaining = p.n - base;
-        for (int i = lane; i < TILE; i += 32) buf[i] = (i < remaining) ? p.x[base + i] : T(0);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[st]);
-      }
-    }
-  }
-
-  if (warp == NWARPS + 2) {
-    // ================= STORE warp: bulk stores + stage recycling =================
-    for (int64 js = 0;; ++js) {
-      const int st = (int)(js % NSTAGE);
-      const unsigned par = (unsigned)((js / NSTAGE) & 1);
-      ptx::mbar_wait(&full[st], par);
-      const int64 tile = s_tile_id[st];
-      if (tile >= p.ntiles) {
-        if (lane == 0) ptx::bulk_wait<0>();
-        { KB200_STATS_FLUSH(); return; }
-      }
-      ptx::mbar_wait(&outready[st], par);
-      const int64 base = tile * TILE;
-      T* const buf = bufs + (size_t)st * TILE;
-      if (p.bulk_store && base + TILE <= p.n) {
-        if (lane == 0) {
-          ptx::bulk_s2g(p.y + base, buf, TILE_BYTES);
-          ptx::bulk_commit();
-          ptx::bulk_wait_read<0>();  // the stage may be overwritten once its bytes have been read
-        }
-      } else {
-        const int64 remaining = p.n - base;
-        for (int i = lane; i < TILE && i < remaining; i += 32) p.y[base + i] = buf[i];
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[st]);
-    }
-  }
-
-  if (warp == NWARPS + 1) {
-    // ================= AGGREGATE warp =================
-    for (int64 j = 0;; ++j) {
-      const int st = (int)(j % NSTAGE);
-      ptx::mbar_wait(&full[st], (unsigned)((j / NSTAGE) & 1));
-      const int64 cur = s_tile_id[st];
-      if (cur >= p.ntiles) {
-        if (lane == 0) mbar_arrive(&aggready[st]);  // pass the end-of-work marker on
-        { KB200_STATS_FLUSH(); return; }
-      }
-      const uint4* src = reinterpret_cast<const uint4*>(bufs + (size_t)st * TILE);
-      T acc[4] = {T(0), T(0), T(0), T(0)};
-      constexpr int NVEC = (int)(TILE_BYTES / 16);
-#pragma unroll 4
-      for (int i = lane; i < NVEC; i += 32) {
-        const uint4 q = src[i];
-        T e[EPV];
-        memcpy(e, &q, 16);
-#pragma unroll
-        for (int k = 0; k < EPV; ++k) acc[k & 3] += e[k];
-      }
-      const T agg = warp_sum_all<T>((acc[0] + acc[1]) + (acc[2] + acc[3]));
-      if (lane == 0) {
-        ptx::st_relaxed_v2(p.desc + cur, to_bits(agg), (p.epoch << 2) | (cur == 0 ? kDescIncl : kDescAgg));
-        s_agg[st] = agg;
-        mbar_arrive(&aggready[st]);
-      }
-    }
-  }
-
-  if (warp >= NWARPS + 3) {
-    // ================= LOOK-BACK warps: one per stage, started as soon as the tile id is known =================
-    // The exclusive prefix of a tile depends on its predecessors only, so the walk overlaps the tile's own load;
-    // consecutive tiles of this CTA resolve concurrently (one warp per stage).
-    const int st = warp - (NWARPS + 3);
-    for (int64 k = 0;; ++k) {
-      const unsigned par = (unsigned)(k & 1);
-      ptx::mbar_wait(&idready[st], par);
-      const int64 cur = s_tile_id[st];
-      if (cur >= p.ntiles) return;
-      T excl = T(0);
-      if (cur > 0 && !(p.dbg_flags & 1)) excl = lookback_sum<T, LBW>(p.desc, cur, p.epoch, lane, p.spin_sleep_ns, p.dbg_flags & 8 KB200_STATS_PASS);
-#ifdef B200_SWEEP
-      const long long t_w2 = clock64();
-#endif
-      ptx::mbar_wait(&aggready[st], par);
-#ifdef B200_SWEEP
-      if (lane == 0) KB200_STAT_ADD(7, clock64() - t_w2);
-#endif
-      if (lane == 0) {
-        const T agg = s_agg[st];
-        if (cur > 0) ptx::st_relaxed_v2(p.desc + cur, to_bits((T)(excl + agg)), (p.epoch << 2) | kDescIncl);
-        s_prefix[st] = excl;
-        if (cur == p.ntiles - 1) {
-          const T total = excl + agg;
-          if (p.total0) *p.total0 = total;
-          if (p.total1) *p.total1 = total;
-        }
-        mbar_arrive(&prefready[st]);
-      }
-    }
-  }
-
-  // ================= compute warps =================
-  const T seed = scan_seed(p);
-  for (int64 j = 0;; ++j) {
-    const int st = (int)(j % NSTAGE);
-    const unsigned par = (unsigned)((j / NSTAGE) & 1);
-#ifdef B200_SWEEP
-    const long long t_w0 = clock64();
-#endif
-    ptx::mbar_wait(&full[st], par);
-#ifdef B200_SWEEP
-    if (tid == 0) { KB200_STAT_ADD(5, clock64() - t_w0); KB200_STAT_ADD(6, 1); }
-#endif
-    const int64 cur = s_tile_id[st];
-    if (cur >= p.ntiles) break;
-    T* const buf = bufs + (size_t)st * TILE;
-    T v[ITEMS];
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(buf + (size_t)tid * ITEMS);
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        const uint4 q = src[k];
-        memcpy(&v[k * EPV], &q, 16);
-      }
-    }
-    T tsum = T(0);
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) tsum += v[k];
-    const T tincl = warp_incl_scan(tsum, lane);
-    if (lane == 31) s_warp[warp] = tincl;
-    named_bar_sync(1, CBLOCK);
-    T woff = T(0);  // exclusive offset of this warp inside the tile: every warp folds the <=32 warp totals itself
-    {
-      const T w = lane < NWARPS ? s_warp[lane] : T(0);
-      const T wi = warp_incl_scan(w, lane);
-      woff = shfl_idx((T)(wi - w), warp);
-    }
-#ifdef B200_SWEEP
-    const long long t_w1 = clock64();
-#endif
-    ptx::mbar_wait(&prefready[st], par);
-#ifdef B200_SWEEP
-    if (tid == 0) KB200_STAT_ADD(4, clock64() - t_w1);
-#endif
-    T run = seed + s_prefix[st] + woff + (tincl - tsum);
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-      const T in = v[k];
-      if (INCLUSIVE) { run += in; v[k] = run; } else { v[k] = run; run += in; }
-    }
-    {
-      uint4* dst = reinterpret_cast<uint4*>(buf + (size_t)tid * ITEMS);
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        uint4 q;
-        memcpy(&q, &v[k * EPV], 16);
-        dst[k] = q;
-      }
-    }
-    ptx::fence_proxy_async_smem();
-    named_bar_sync(1, CBLOCK);  // also orders the s_warp reads above before the next tile's writes
-    if (tid == 0) mbar_arrive(&outready[st]);
-  }
-  KB200_STATS_FLUSH();
-}
-
-// WS = true: warp-specialised kernel (BLOCK compute threads + one DMA warp); false: the uniform kernel
+// WS = 2: the warp-specialised kernel above (16-byte aligned Views); 0: the uniform kernel; 1/3/4: sweep-only variants
 template <class T, int BLOCK, int NV, int NBUF, int LBW, bool INCLUSIVE, int WS = 0>
 struct ContigScanLaunch {
   static constexpr int ITEMS = NV * 16 / (int)sizeof(T);
@@ -1206,12 +818,16 @@ struct ContigScanLaunch {
   static constexpr int THREADS = WS == 4 ? BLOCK + 96 + 32 * NBUF : WS == 3 ? BLOCK + 128 : (WS == 2 ? BLOCK + 96 : (WS == 1 ? BLOCK + 32 : BLOCK));
 
   static auto kernel() {
+#ifdef B200_SWEEP
     if constexpr (WS == 4) return contig_scan_ws4_kernel<T, BLOCK, NV, NBUF, LBW, INCLUSIVE>;
     else if constexpr (WS == 3) return contig_scan_ws3_kernel<T, BLOCK, NV, NBUF, LBW, INCLUSIVE>;
-    else if constexpr (WS == 2) return contig_scan_ws2_kernel<T, BLOCK, NV, NBUF, LBW, INCLUSIVE>;
     else if constexpr (WS == 1) return contig_scan_ws_kernel<T, BLOCK, NV, NBUF, LBW, INCLUSIVE>;
+    else
+#endif
+    if constexpr (WS == 2) return contig_scan_ws2_kernel<T, BLOCK, NV, NBUF, LBW, INCLUSIVE>;
     else return contig_scan_kernel<T, BLOCK, NV, NBUF, LBW, INCLUSIVE>;
   }
+  static auto rounds_kernel() { return contig_scan_ws2_kernel<T, BLOCK, NV, NBUF, LBW, INCLUSIVE, true>; }
   static int resident_blocks_per_sm() {
     static int cached = 0;
     if (cached == 0) {
@@ -1222,6 +838,63 @@ struct ContigScanLaunch {
       cached = nb > 0 ? nb : 1;
     }
     return cached;
+  }
+
+  // One rank of a block-cyclic distributed scan: x/y = this rank's rounds back to back (n elements), every rank runs
+  // `nrounds` rounds of `tpr` tiles (tiles past n are empty but still take part in the exchange).  16-byte aligned Views.
+  static int run_rounds(b200_instance* inst, const RoundPeers& peers, int64 tpr, int64 nrounds, const T* x, T* y, int64 n, T* total_host, T* total_dev) {
+    static_assert(WS == 2, "the rounds kernel is the warp-specialised one");
+    HostRuntime rt(inst);
+    int rc;
+    if (nrounds <= 0) {
+      if (total_dev && (rc = b200_memset_async(inst, total_dev, 0, sizeof(T)))) return rc;
+      if (total_host) {
+        if ((rc = rt.fence("kb200::parallel_scan (empty)"))) return rc;
+        *total_host = T(0);
+      }
+      return 0;
+    }
+    static int bps_cached = 0;
+    if (bps_cached == 0) {
+      auto k = rounds_kernel();
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, THREADS + 32, SMEM);
+      bps_cached = nb > 0 ? nb : 1;
+    }
+    const int64 ntiles = nrounds * tpr;
+    const int64 max_grid = (int64)rt.sm_count() * bps_cached;
+    const int grid = (int)(ntiles < max_grid ? ntiles : max_grid);
+    // live rounds <= 1 + grid * NBUF / tpr must fit the descriptor ring
+    if ((int64)grid * NBUF / tpr + 2 + kRoundLookback > kRoundRing) return b200_report_error(B200_EINVAL, "kb200::parallel_scan (rounds): tiles per round too small for the round ring");
+    ScanContigParams<T> p;
+    memset(&p, 0, sizeof p);
+    p.x = x; p.y = y; p.n = n; p.ntiles = ntiles; p.seed = T(0); p.seed_count = 0;
+    void* desc = nullptr;
+    if ((rc = b200_scratch_get(inst, B200_SCRATCH_SCAN_DESC, (size_t)ntiles * sizeof(ScanDesc16), &desc, nullptr))) return rc;
+    p.desc = reinterpret_cast<ScanDesc16*>(desc);
+    uint64_t epoch = 0, cbase = 0;
+    if ((rc = b200_scan_begin(inst, (uint64_t)ntiles + (uint64_t)grid, &epoch, &cbase, &p.counter))) return rc;
+    p.epoch = epoch; p.counter_base = cbase;
+    void *slot_dev = nullptr, *slot_host = nullptr, *unused_p = nullptr;
+    unsigned* unused_t = nullptr;
+    if (total_host && (rc = rt.reduce_scratch(0, sizeof(T), true, &unused_p, &unused_t, &slot_dev, &slot_host))) return rc;
+    p.total0 = total_host ? reinterpret_cast<T*>(slot_dev) : total_dev;
+    p.total1 = total_host ? total_dev : nullptr;
+    p.bulk_load = 1; p.bulk_store = 1;
+    p.tpr = tpr; p.rank = peers.rank; p.world = peers.world; p.rtag_base = peers.rtag_base;
+    p.rdesc = peers.rdesc; p.mbox = peers.mbox; p.racc = peers.racc;
+    if (tpr > 32768) return b200_report_error(B200_EINVAL, "kb200::parallel_scan (rounds): at most 32768 tiles per round");
+    for (int q = 0; q < peers.world; ++q) p.peer_mbox[q] = peers.peer_mbox[q];
+    p.err = peers.err;
+    p.timeout_ns = 20ull * 1000000000ull;
+    rounds_kernel()<<<grid, THREADS + 32, SMEM, rt.stream()>>>(p);
+    if ((rc = rt.check_launch("kb200::contig_scan_ws2_kernel (rounds)"))) return rc;
+    if (total_host) {
+      if ((rc = rt.fence("kb200::parallel_scan: fence to hand the total to the host"))) return rc;
+      memcpy(total_host, slot_host, sizeof(T));
+    }
+    return 0;
   }
 
   static int run(b200_instance* inst, const T* x, T* y, int64 n, T seed, const T* seed_dev, T* total_host, T* total_dev,

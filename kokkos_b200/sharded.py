@@ -44,6 +44,30 @@ def shard_bounds(n: int, world: int, rank: int, align: int = 1) -> tuple[int, in
     return cut(rank), cut(rank + 1)
 
 
+def cyclic_blocks(n_global: int, block: int, world: int, rank: int) -> list[tuple[int, int]]:
+    """Global [begin, end) ranges owned by `rank` under the block-cyclic distribution of the fused scan
+    (kb200/impl/ScanChunked.hpp): global block c lives on rank c % world as local block c // world; local blocks are stored
+    back to back in that order.  Only the last global block may be short."""
+    if world < 1 or not (0 <= rank < world) or n_global < 0 or block < 1:
+        raise ValueError("cyclic_blocks: bad arguments")
+    nblocks = -(-n_global // block)
+    return [(c * block, min(n_global, (c + 1) * block)) for c in range(rank, nblocks, world)]
+
+
+def cyclic_take(global_array: np.ndarray, block: int, world: int, rank: int) -> np.ndarray:
+    """The local part (owned blocks, concatenated) of a global array."""
+    parts = [global_array[b:e] for b, e in cyclic_blocks(global_array.size, block, world, rank)]
+    return np.concatenate(parts) if parts else global_array[:0].copy()
+
+
+def cyclic_put(global_out: np.ndarray, local: np.ndarray, block: int, world: int, rank: int) -> None:
+    """Inverse of cyclic_take: scatter a rank's local part into the global array."""
+    off = 0
+    for b, e in cyclic_blocks(global_out.size, block, world, rank):
+        global_out[b:e] = local[off:off + (e - b)]
+        off += e - b
+
+
 def join_minloc(dest: tuple, src: tuple) -> tuple:
     """MinLoc::join (Kokkos_Parallel_Reduce.hpp:441-449) on (val, loc) pairs."""
     if src[0] < dest[0]:
