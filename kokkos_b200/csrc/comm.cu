@@ -229,9 +229,17 @@ int comm_collective(b200_comm* C, const char* where, const void* src, void* dst,
 }
 
 // tiles per round of the rounds kernel: a round (= the block of the block-cyclic distribution) is tpr tiles of 18 KiB
-int64_t round_tpr() { return b200_tune("comm.tpr", 256); }
+int64_t round_tpr() { return b200_tune("comm.tpr", 128); }  // 128 x 18 KiB = 2.25 MiB per round and rank (profiles/r02_cyclic_scan_probe.log)
 template <class T>
-int64_t round_block_elems() { return round_tpr() * ContigScanLaunch<T, 128, 9, 4, 1, false, 2>::TILE; }
+int64_t round_block_elems() {
+  int64_t tile = ContigScanLaunch<T, 128, 9, 4, 1, false, 2>::TILE;
+#ifdef B200_SWEEP
+  const int tiles[] = {128 * 9, 128 * 7, 128 * 5, 64 * 9, 256 * 9, 128 * 9};
+  const int c = b200_tune("comm.cfg", 0);
+  if (c >= 0 && c <= 5) tile = (int64_t)tiles[c] * 16 / (int64_t)sizeof(T);
+#endif
+  return round_tpr() * tile;
+}
 
 template <class T, bool INCL>
 int comm_scan(b200_comm* C, const char* where, const T* x, T* y, int64_t n_global, T* total_host, T* total_dev) {
@@ -270,6 +278,16 @@ int comm_scan(b200_comm* C, const char* where, const T* x, T* y, int64_t n_globa
   peers.err = C->err_dev;
   C->round_tag += (unsigned)nsteps;
   if (C->round_tag == 0) C->round_tag = 1;
+#ifdef B200_SWEEP
+  switch (b200_tune("comm.cfg", 0)) {  // tile shape experiments (same tile BYTES per round only if tpr is scaled by the caller)
+    case 1: return ContigScanLaunch<T, 128, 7, 5, 1, INCL, 2>::run_rounds(C->inst, peers, round_tpr(), nsteps, x, y, n_local, total_host, total_dev);
+    case 2: return ContigScanLaunch<T, 128, 5, 7, 1, INCL, 2>::run_rounds(C->inst, peers, round_tpr(), nsteps, x, y, n_local, total_host, total_dev);
+    case 3: return ContigScanLaunch<T, 64, 9, 8, 1, INCL, 2>::run_rounds(C->inst, peers, round_tpr(), nsteps, x, y, n_local, total_host, total_dev);
+    case 4: return ContigScanLaunch<T, 256, 9, 2, 1, INCL, 2>::run_rounds(C->inst, peers, round_tpr(), nsteps, x, y, n_local, total_host, total_dev);
+    case 5: return ContigScanLaunch<T, 128, 9, 4, 2, INCL, 2>::run_rounds(C->inst, peers, round_tpr(), nsteps, x, y, n_local, total_host, total_dev);
+    default: break;
+  }
+#endif
   return LR::run_rounds(C->inst, peers, round_tpr(), nsteps, x, y, n_local, total_host, total_dev);
 }
 
@@ -433,7 +451,7 @@ int b200_comm_cyclic_layout(b200_comm* C, int elem_bytes, int64_t n_global, int6
   if (!C) return b200_set_error(B200_ENOTINIT, where, nullptr);
   if ((elem_bytes != 4 && elem_bytes != 8) || n_global < 0) return b200_set_error(B200_EINVAL, where, "element size must be 4 or 8, length >= 0");
   const int64_t block = b200_tune("comm.scan_algo", 0) == 1 ? (int64_t)C->grid * 384 * (9 * 16 / elem_bytes)
-                                                            : round_tpr() * 128 * (9 * 16 / elem_bytes);
+                                                            : (elem_bytes == 8 ? round_block_elems<int64>() : round_block_elems<int>());
   const int64_t nblocks = (n_global + block - 1) / block;
   int64_t nl = 0;
   for (int64_t c = C->rank; c < nblocks; c += C->world) nl += (c == nblocks - 1) ? (n_global - c * block) : block;
