@@ -63,6 +63,7 @@ int b200_device_props(b200_instance* inst, b200_props* out);
 int b200_device_count(int* count);
 void* b200_instance_stream(b200_instance* inst);               /* the cudaStream_t           */
 uint32_t b200_instance_id(b200_instance* inst);                /* Cuda::impl_instance_id()   */
+int b200_instance_device(b200_instance* inst);                 /* Cuda::cuda_device(); -1 for NULL */
 const char* b200_last_error_string(void);
 const char* b200_version(void);
 

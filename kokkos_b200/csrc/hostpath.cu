@@ -33,10 +33,15 @@ __global__ void carry_add_i64(const long long* seed_in, const long long* total, 
   *seed_out = *seed_in + *total;
 }
 
-int pipe_get(b200_instance* I, HostPipe** out) {
-  static std::mutex m;
+std::mutex g_pipe_mutex;
+std::map<b200_instance*, HostPipe*>& pipe_map() {
   static std::map<b200_instance*, HostPipe*> pipes;
-  std::lock_guard<std::mutex> lock(m);
+  return pipes;
+}
+
+int pipe_get(b200_instance* I, HostPipe** out) {
+  std::lock_guard<std::mutex> lock(g_pipe_mutex);
+  auto& pipes = pipe_map();
   auto it = pipes.find(I);
   if (it != pipes.end()) { *out = it->second; return 0; }
   HostPipe* P = new HostPipe();
@@ -59,6 +64,30 @@ int pipe_get(b200_instance* I, HostPipe** out) {
   return 0;
 }
 
+}  // namespace
+
+// b200_finalize: the staging pipeline dies with its instance (a later instance at the same address must not inherit it)
+void b200_hostpath_release(b200_instance* I) {
+  std::lock_guard<std::mutex> lock(g_pipe_mutex);
+  auto& pipes = pipe_map();
+  auto it = pipes.find(I);
+  if (it == pipes.end()) return;
+  HostPipe* P = it->second;
+  pipes.erase(it);
+  if (P->in) cudaStreamSynchronize(P->in);
+  if (P->out) cudaStreamSynchronize(P->out);
+  for (int k = 0; k < kDepth; ++k) {
+    if (P->din[k]) cudaFree(P->din[k]);
+    if (P->dout[k]) cudaFree(P->dout[k]);
+    if (P->ready) { cudaEventDestroy(P->loaded[k]); cudaEventDestroy(P->computed[k]); cudaEventDestroy(P->drained[k]); cudaEventDestroy(P->consumed[k]); }
+  }
+  if (P->carry) cudaFree(P->carry);
+  if (P->in) cudaStreamDestroy(P->in);
+  if (P->out) cudaStreamDestroy(P->out);
+  delete P;
+}
+
+namespace {
 #define CU(expr)                                                                \
   do {                                                                          \
     cudaError_t e__ = (expr);                                                   \

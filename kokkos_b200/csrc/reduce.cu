@@ -27,12 +27,14 @@ struct MinMaxOp {
     if (x > a.max_val) a.max_val = x;
   }
 };
-struct MinLocOp { template <class V, class T> KB200_DEVICE_FUNCTION static void apply(V& a, T x, int64 i) { if (x < a.val) { a.val = x; a.loc = i; } } };
-struct MaxLocOp { template <class V, class T> KB200_DEVICE_FUNCTION static void apply(V& a, T x, int64 i) { if (x > a.val) { a.val = x; a.loc = i; } } };
+// loc reducers: equal extrema keep the LOWEST location whatever order a thread meets them in (the scalar head elements of
+// an unaligned View are folded after the vector body, and they carry the lowest indices)
+struct MinLocOp { template <class V, class T> KB200_DEVICE_FUNCTION static void apply(V& a, T x, int64 i) { if (x < a.val || (x == a.val && i < a.loc)) { a.val = x; a.loc = i; } } };
+struct MaxLocOp { template <class V, class T> KB200_DEVICE_FUNCTION static void apply(V& a, T x, int64 i) { if (x > a.val || (x == a.val && i < a.loc)) { a.val = x; a.loc = i; } } };
 struct MinMaxLocOp {
   template <class V, class T> KB200_DEVICE_FUNCTION static void apply(V& a, T x, int64 i) {
-    if (x < a.min_val) { a.min_val = x; a.min_loc = i; }
-    if (x > a.max_val) { a.max_val = x; a.max_loc = i; }
+    if (x < a.min_val || (x == a.min_val && i < a.min_loc)) { a.min_val = x; a.min_loc = i; }
+    if (x > a.max_val || (x == a.max_val && i < a.max_loc)) { a.max_val = x; a.max_loc = i; }
   }
 };
 

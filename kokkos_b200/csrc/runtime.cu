@@ -49,6 +49,22 @@ int b200_set_error(int code, const char* where, const char* detail) {
   return code;
 }
 
+// makes `device` current for a scope and restores the caller's device (multi-GPU processes: every entry that allocates,
+// copies or launches acts on the instance's device, never on whatever happens to be current)
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int device) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != device) {
+      cudaSetDevice(device);
+      prev = cur;
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 #define CU_TRY(expr, where)                                            \
   do {                                                                 \
     cudaError_t e__ = (expr);                                          \
@@ -72,7 +88,7 @@ static int instance_setup(int device, cudaStream_t stream, bool owns_stream, b20
   int ndev = 0;
   CU_TRY(cudaGetDeviceCount(&ndev), "b200_init");
   if (device < 0 || device >= ndev) return b200_set_error(B200_EINVAL, "b200_init", "device id out of range");
-  CU_TRY(cudaSetDevice(device), "b200_init");
+  DeviceGuard guard(device);
   cudaDeviceProp p;
   CU_TRY(cudaGetDeviceProperties(&p, device), "b200_init");
   if (p.major != 10)  // kernels are sm_100a SASS only: anything else cannot run them
@@ -144,7 +160,8 @@ int b200_instance_create(int device, void* cuda_stream, b200_instance** out) {
 
 int b200_finalize(b200_instance* I) {
   if (!I) return b200_set_error(B200_ENOTINIT, "b200_finalize", nullptr);
-  cudaSetDevice(I->device);
+  DeviceGuard guard(I->device);
+  b200_hostpath_release(I);
   if (I->stream || !I->owns_stream) cudaStreamSynchronize(I->stream);
   if (I->partials) cudaFree(I->partials);
   if (I->flags) cudaFree(I->flags);
@@ -178,6 +195,7 @@ int b200_device_props(b200_instance* I, b200_props* out) {
 void* b200_instance_stream(b200_instance* I) { return I ? (void*)I->stream : nullptr; }
 uint32_t b200_instance_id(b200_instance* I) { return I ? I->id : 0; }
 int b200_instance_sm_count(b200_instance* I) { return I ? I->props.sm_count : 0; }
+int b200_instance_device(b200_instance* I) { return I ? I->device : -1; }
 
 // ---------------------------------------------------------------- memory
 int b200_malloc(b200_instance* I, size_t bytes, void** out) {
@@ -185,7 +203,7 @@ int b200_malloc(b200_instance* I, size_t bytes, void** out) {
   if (!out) return b200_set_error(B200_EINVAL, "b200_malloc", "out is NULL");
   *out = nullptr;
   if (bytes == 0) return 0;  // zero-length View: null data pointer, as the reference
-  CU_TRY(cudaSetDevice(I->device), "b200_malloc");
+  DeviceGuard guard(I->device);
   cudaError_t e = cudaMalloc(out, bytes);
   if (e == cudaErrorMemoryAllocation) {
     cudaGetLastError();
@@ -199,7 +217,7 @@ int b200_malloc(b200_instance* I, size_t bytes, void** out) {
 int b200_free(b200_instance* I, void* ptr) {
   if (!I) return b200_set_error(B200_ENOTINIT, "b200_free", nullptr);
   if (!ptr) return 0;
-  CU_TRY(cudaSetDevice(I->device), "b200_free");
+  DeviceGuard guard(I->device);
   CU_TRY(cudaFree(ptr), "b200_free");
   return 0;
 }
@@ -221,6 +239,7 @@ int b200_memset_async(b200_instance* I, void* dst, int byte, size_t bytes) {
   if (!I) return b200_set_error(B200_ENOTINIT, "b200_memset_async", nullptr);
   if (bytes == 0) return 0;
   if (!dst) return b200_set_error(B200_EINVAL, "b200_memset_async", "dst is NULL");
+  DeviceGuard guard(I->device);
   CU_TRY(cudaMemsetAsync(dst, byte, bytes, I->stream), "b200_memset_async");
   return 0;
 }
@@ -228,6 +247,7 @@ static int copy_async(b200_instance* I, void* dst, const void* src, size_t bytes
   if (!I) return b200_set_error(B200_ENOTINIT, where, nullptr);
   if (bytes == 0) return 0;
   if (!dst || !src) return b200_set_error(B200_EINVAL, where, "NULL pointer");
+  DeviceGuard guard(I->device);
   CU_TRY(cudaMemcpyAsync(dst, src, bytes, kind, I->stream), where);
   return 0;
 }
@@ -238,6 +258,7 @@ int b200_memcpy_d2d_async(b200_instance* I, void* d, const void* s, size_t n) { 
 // ---------------------------------------------------------------- scratch
 static int grow(b200_instance* I, void** ptr, size_t* have, size_t want, bool zero, const char* what) {
   if (want <= *have) return 0;
+  DeviceGuard guard(I->device);
   // growth is a cold path: drain the stream so nothing in flight still uses the old block
   CU_TRY(cudaStreamSynchronize(I->stream), what);
   if (*ptr) CU_TRY(cudaFree(*ptr), what);
@@ -379,7 +400,7 @@ int b200_chunk_begin(b200_instance* I, uint64_t nsteps, unsigned* tag_base, unsi
   std::lock_guard<std::mutex> lock(I->mutex);
   if (!I->chunk_desc) {  // first use: 64 KiB of LL descriptors (zero = tag 0 = never valid) + one pinned error word
     constexpr size_t kBytes = 16 * 256 * 16;
-    CU_TRY(cudaSetDevice(I->device), "b200_chunk_begin");
+    DeviceGuard guard(I->device);
     CU_TRY(cudaMalloc((void**)&I->chunk_desc, kBytes), "b200_chunk_begin");
     CU_TRY(cudaMemsetAsync(I->chunk_desc, 0, kBytes, I->stream), "b200_chunk_begin");
     CU_TRY(cudaHostAlloc((void**)&I->chunk_err, 64, cudaHostAllocMapped), "b200_chunk_begin");
@@ -400,6 +421,7 @@ int b200_launch(b200_instance* I, const void* func, unsigned gx, unsigned gy, un
                 unsigned bz, size_t smem, void** args) {
   if (!I) return b200_set_error(B200_ENOTINIT, "b200_launch", nullptr);
   if (!func) return b200_set_error(B200_EINVAL, "b200_launch", "func is NULL");
+  DeviceGuard guard(I->device);
   CU_TRY(cudaLaunchKernel(func, dim3(gx, gy, gz), dim3(bx, by, bz), args, smem, I->stream), "b200_launch");
   return 0;
 }

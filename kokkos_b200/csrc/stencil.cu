@@ -433,8 +433,8 @@ int launch_tma(b200_instance* I, const double* u, double* v_out, int n0, int n1,
   HostRuntime rt(I);
   auto kern = v_out ? stencil7_tma_kernel<BJ, NS, CT, true, N0T, PW> : stencil7_tma_kernel<BJ, NS, CT, false, N0T, PW>;
   const size_t smem = (size_t)NS * stencil_stage_elems(BJ, n0) * sizeof(double) + 2 * NS * sizeof(unsigned long long);
-  static size_t smem_set_[2] = {0, 0};
-  size_t& smem_set = smem_set_[v_out ? 1 : 0];  // grow-only opt-in, like the reference's func-attr cache (KernelLaunch.hpp:131-145)
+  static size_t smem_set_[64][2] = {};
+  size_t& smem_set = smem_set_[I->device & 63][v_out ? 1 : 0];  // grow-only opt-in, like the reference's func-attr cache (KernelLaunch.hpp:131-145)
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return b200_report_error((int)e, where);

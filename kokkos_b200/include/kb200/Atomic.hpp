@@ -324,9 +324,13 @@ KB200_DEVICE_FUNCTION T atomic_exchange(T* p, T v) {
 }
 template <class T>
 KB200_DEVICE_FUNCTION T atomic_compare_exchange(T* p, T compare, T v) {
-  if constexpr (sizeof(T) == 2 || sizeof(T) == 4 || sizeof(T) == 8 || sizeof(T) == 16) {
+  // one hardware CAS when the object is naturally aligned for it; a 16-byte object with 8-byte alignment may sit at an odd
+  // 8-byte offset, where atom.cas.b128 faults (misaligned address, sticky): it takes the locked path like other large objects
+  if constexpr (sizeof(T) == 2 || sizeof(T) == 4 || sizeof(T) == 8 || (sizeof(T) == 16 && alignof(T) >= 16)) {
     using W = typename Impl::word_of<sizeof(T)>::type;
     return Impl::from_word<T, W>(Impl::atom_cas(reinterpret_cast<W*>(p), Impl::as_word<T>(compare), Impl::as_word<T>(v)));
+  } else if constexpr (sizeof(T) > 8) {
+    return Impl::locked_rmw(p, [=](const T& o) { return o == compare ? v : o; });
   } else {
     return Impl::cas_loop(p, [=](T o) { return o == compare ? v : o; });
   }
@@ -340,11 +344,11 @@ KB200_DEVICE_FUNCTION T atomic_load(const T* p) {
     return Impl::from_word<T, W>(Impl::atom_cas(reinterpret_cast<W*>(const_cast<T*>(p)), W{0, 0}, W{0, 0}));
   } else if constexpr (sizeof(T) == 8) {
     unsigned long long w;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");  // generic address: global or team scratch
     return Impl::from_word<T, unsigned long long>(w);
   } else if constexpr (sizeof(T) == 4) {
     unsigned w;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(w) : "l"(p) : "memory");
     return Impl::from_word<T, unsigned>(w);
   } else {
     return *reinterpret_cast<const volatile T*>(p);
@@ -355,9 +359,9 @@ KB200_DEVICE_FUNCTION void atomic_store(T* p, T v) {
   if constexpr (sizeof(T) > 8) {
     (void)Impl::cas_loop(p, [=](const T&) { return v; });
   } else if constexpr (sizeof(T) == 8) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(Impl::as_word<T>(v)) : "memory");
+    asm volatile("st.relaxed.gpu.u64 [%0], %1;" ::"l"(p), "l"(Impl::as_word<T>(v)) : "memory");
   } else if constexpr (sizeof(T) == 4) {
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(Impl::as_word<T>(v)) : "memory");
+    asm volatile("st.relaxed.gpu.u32 [%0], %1;" ::"l"(p), "r"(Impl::as_word<T>(v)) : "memory");
   } else {
     *reinterpret_cast<volatile T*>(p) = v;
   }

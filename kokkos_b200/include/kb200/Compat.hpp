@@ -252,6 +252,7 @@ template <class T> inline constexpr bool is_memory_space_v = is_memory_space<T>:
 // used directly by core/unit_test/TestAtomicOperations.hpp:336-380): old value returned, new value = (old >= wrap) ? 0 : old + 1
 // resp. (old == 0 || old > wrap) ? wrap : old - 1.  Memory order / scope tags are accepted (relaxed, device scope is what the
 // Kokkos wrappers always request: core/src/Kokkos_Atomics_Desul_Wrapper.hpp:72-148).
+#ifdef KB200_AS_KOKKOS  // (with the real desul in the translation unit -- the Kokkos::B200 adapter -- its own definitions are used)
 namespace desul {
 struct MemoryOrderRelaxed {};
 struct MemoryOrderSeqCst {};
@@ -286,4 +287,5 @@ KB200_FORCEINLINE_FUNCTION T atomic_fetch_dec_mod(T* p, T wrap, Order, Scope) {
 #define KOKKOS_IMPL_DISABLE_UNREACHABLE_WARNINGS_POP()
 #define KOKKOS_IMPL_DISABLE_DEPRECATED_WARNINGS_PUSH()
 #define KOKKOS_IMPL_DISABLE_DEPRECATED_WARNINGS_POP()
+#endif  // KB200_AS_KOKKOS
 #endif

@@ -45,9 +45,9 @@ KB200_TEAM_FUNCTION unsigned vmask() {
   )
   return 0xffffffffu;
 }
-template <class T> KB200_TEAM_FUNCTION T up(const T& v, int d) { KB200_TEAM_DEVICE_ONLY(return shfl_up(v, (unsigned)d, vmask());) return v; }
-template <class T> KB200_TEAM_FUNCTION T down(const T& v, int d) { KB200_TEAM_DEVICE_ONLY(return shfl_down(v, (unsigned)d, vmask());) return v; }
-template <class T> KB200_TEAM_FUNCTION T idx(const T& v, int l) { KB200_TEAM_DEVICE_ONLY(return shfl_idx(v, l, vmask());) return v; }
+template <class T> KB200_TEAM_FUNCTION T up(const T& v, int d) { KB200_TEAM_DEVICE_ONLY(return ::kb200::Impl::shfl_up(v, (unsigned)d, vmask());) return v; }
+template <class T> KB200_TEAM_FUNCTION T down(const T& v, int d) { KB200_TEAM_DEVICE_ONLY(return ::kb200::Impl::shfl_down(v, (unsigned)d, vmask());) return v; }
+template <class T> KB200_TEAM_FUNCTION T idx(const T& v, int l) { KB200_TEAM_DEVICE_ONLY(return ::kb200::Impl::shfl_idx(v, l, vmask());) return v; }
 KB200_TEAM_FUNCTION void syncwarp() { KB200_TEAM_DEVICE_ONLY(__syncwarp(vmask());) }
 template <class Red> KB200_TEAM_FUNCTION void block_red(const Red& red, typename Red::value_type& v, void* smem) {
   KB200_TEAM_DEVICE_ONLY(block_reduce(red, v, smem);)
@@ -127,6 +127,12 @@ class B200TeamMember {
 
   KB200_TEAM_FUNCTION int league_rank() const { return m_league_rank; }
   KB200_TEAM_FUNCTION int league_size() const { return m_league_size; }
+  // raw scratch pools of this team (level 0 = shared memory, 1 = global arena): base pointer and bytes, for layers that
+  // hand out their own scratch-space handle type over the same memory (kokkos_b200/adapter)
+  KB200_TEAM_FUNCTION void* impl_scratch_ptr(int level) const { return level == 0 ? (void*)m_l0 : (void*)m_l1; }
+  KB200_TEAM_FUNCTION size_t impl_scratch_bytes(int level) const {
+    return level == 0 ? m_l0_team + m_l0_thread * (size_t)Impl::tm::ny() : m_l1_team + m_l1_thread * (size_t)Impl::tm::ny();
+  }
   KB200_TEAM_FUNCTION int team_rank() const { return Impl::tm::ty(); }
   KB200_TEAM_FUNCTION int team_size() const { return Impl::tm::ny(); }
   KB200_TEAM_FUNCTION int impl_vector_lane() const { return Impl::tm::tx(); }

@@ -211,7 +211,15 @@ class View : public Impl::ViewStrides<Impl::view_is_strided<Props...>::value> {
   template <class D2, class... P2, class = std::enable_if_t<std::is_convertible<typename View<D2, P2...>::pointer_type, pointer_type>::value &&
                                                             View<D2, P2...>::rank == rank>>
   KB200_INLINE_FUNCTION View(const View<D2, P2...>& o) : m_data(o.data()), m_rec(is_managed ? o.impl_record() : nullptr) {
+    using Src = View<D2, P2...>;
+    // layout compatibility, as the reference's ViewMapping assignability rules (core/src/View/Kokkos_ViewMapping.hpp): same
+    // layout, anything into LayoutStride, and Left <-> Right only where both describe the same memory (rank <= 1)
+    static_assert(is_strided || std::is_same<array_layout, typename Src::array_layout>::value || (rank <= 1 && !Src::is_strided),
+                  "View assignment must have compatible layouts (LayoutLeft <-> LayoutRight differ for rank > 1; a strided View "
+                  "cannot be assigned to a contiguous layout)");
     for (int r = 0; r < 8; ++r) m_ext[r] = o.extent(r);
+    if constexpr (is_strided)
+      for (int r = 0; r < 8; ++r) this->m_stride[r] = r < rank ? o.stride(r) : 0;
     retain();
   }
   KB200_INLINE_FUNCTION View& operator=(const View& o) {
@@ -305,7 +313,11 @@ class View : public Impl::ViewStrides<Impl::view_is_strided<Props...>::value> {
   std::string label() const { return m_rec ? m_rec->label : std::string(); }
   int use_count() const { return m_rec ? m_rec->refcount : 0; }
   KB200_INLINE_FUNCTION Impl::AllocRecord* impl_record() const { return m_rec; }
-  void impl_window(size_t offset, size_t count) { m_data += offset; m_ext[0] = count; }
+  void impl_window(size_t offset, size_t count) {
+    if constexpr (is_strided) m_data += offset * this->m_stride[0];
+    else m_data += offset;
+    m_ext[0] = count;
+  }
   // subview construction: share `parent`'s allocation record, point at `ptr`, take extents (and strides) as given
   template <class Parent>
   void impl_assign_strided(const Parent& parent, pointer_type ptr, const size_t* ext, const size_t* strides) {

@@ -47,14 +47,15 @@ KB200_DEVICE_FUNCTION void array_block_reduce(const F& f, T (&acc)[CAP], int cou
   const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
   const int nthreads = blockDim.x * blockDim.y * blockDim.z;
   const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
+  const int live = (nthreads - (warp << 5)) < 32 ? (nthreads - (warp << 5)) : 32;  // lanes of this warp that exist
+  const unsigned mask = live >= 32 ? kFullMask : ((1u << live) - 1u);
   T tmp[CAP];
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
     for (int c = 0; c < CAP; ++c)
-      if (c < count) tmp[c] = shfl_down(acc[c], d);
-    // lanes past the end of a partial last warp hold the identity (they never ran an iteration), so joining them is harmless
-    if (lane + d < 32) ArrayOps<F, T>::join(f, acc, tmp, count);
+      if (c < count) tmp[c] = ::kb200::Impl::shfl_down(acc[c], d, mask);
+    if (lane + d < live) ArrayOps<F, T>::join(f, acc, tmp, count);  // never join a lane that does not exist
   }
   if (nwarps == 1) return;
   if (lane == 0)
@@ -68,7 +69,7 @@ KB200_DEVICE_FUNCTION void array_block_reduce(const F& f, T (&acc)[CAP], int cou
     for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
       for (int c = 0; c < CAP; ++c)
-        if (c < count) tmp[c] = shfl_down(acc[c], d);
+        if (c < count) tmp[c] = ::kb200::Impl::shfl_down(acc[c], d);
       if (lane + d < 32) ArrayOps<F, T>::join(f, acc, tmp, count);
     }
   }

@@ -85,7 +85,7 @@ KB200_DEVICE_FUNCTION void warp_reduce(const Red& red, typename Red::value_type&
     const int lane = (threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) & 31;
 #pragma unroll
     for (int d = 1; d < kWarp; d <<= 1) {
-      V hi = shfl_down(v, d, mask);  // value of lane+d: the HIGHER-ranked operand
+      V hi = ::kb200::Impl::shfl_down(v, d, mask);  // value of lane+d: the HIGHER-ranked operand
       // a partner beyond the live lanes contributes nothing; within a full warp an out-of-range partner
       // returns the lane's own value, whose result lane 0's fold never consumes
       if (nl >= kWarp || lane + d < nl) red.join(v, hi);

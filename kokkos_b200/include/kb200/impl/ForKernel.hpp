@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(BLOCK) range_for_kernel(const __grid_constant_
 template <class Body, int BLOCK = 256, int UNROLL = 4>
 struct RangeForLaunch {
   static int resident_blocks_per_sm() {
-    static int cached = 0;
+    static PerDeviceInt cache;
+    int& cached = cache.here();
     if (cached == 0) {
       int nb = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, range_for_kernel<Body, BLOCK, UNROLL>, BLOCK, 0);

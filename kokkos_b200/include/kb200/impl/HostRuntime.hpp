@@ -11,9 +11,35 @@
 namespace kb200 {
 namespace Impl {
 
+// One-time per-kernel set-up (cudaFuncSetAttribute opt-ins, occupancy queries) is per DEVICE: a process may drive several
+// GPUs through B200::on_device / partition_space (core/unit_test/TestMultiGPU.hpp).  `here()` is the slot of the current device.
+struct PerDeviceInt {
+  int v[64] = {};
+  int& here() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return v[d & 63];
+  }
+};
+
+// Every launcher builds one of these first: it makes the instance's device current for the duration of the call (launches,
+// scratch growth and occupancy queries all act on the current device) and restores the caller's device afterwards.
 struct HostRuntime {
   b200_instance* inst;
-  explicit HostRuntime(b200_instance* i) : inst(i) {}
+  int prev_device = -1;
+  explicit HostRuntime(b200_instance* i) : inst(i) {
+    const int want = b200_instance_device(i);
+    int cur = -1;
+    if (want >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != want) {
+      cudaSetDevice(want);
+      prev_device = cur;
+    }
+  }
+  ~HostRuntime() {
+    if (prev_device >= 0) cudaSetDevice(prev_device);
+  }
+  HostRuntime(const HostRuntime&) = delete;
+  HostRuntime& operator=(const HostRuntime&) = delete;
   cudaStream_t stream() const { return static_cast<cudaStream_t>(b200_instance_stream(inst)); }
   int sm_count() const { return b200_instance_sm_count(inst); }
   int reduce_scratch(size_t partial_bytes, size_t value_bytes, bool want_slot, void** partials, unsigned** ticket,

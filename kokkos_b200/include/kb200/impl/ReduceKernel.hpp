@@ -66,7 +66,8 @@ struct RangeReduceLaunch {
   using V = typename Red::value_type;
 
   static int resident_blocks_per_sm() {
-    static int cached = 0;  // per instantiation, like the reference's func-attr cache (KernelLaunch.hpp:131-145)
+    static PerDeviceInt cache;  // per instantiation and device, like the reference's func-attr cache (KernelLaunch.hpp:131-145)
+    int& cached = cache.here();
     if (cached == 0) {
       int nb = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, range_reduce_kernel<Body, Red, BLOCK, UNROLL, MIN_BLOCKS>, BLOCK, 0);

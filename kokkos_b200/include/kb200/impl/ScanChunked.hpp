@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(SCAN_THREADS + RED_WARPS * 32 + 64 + 32 * NSTA
     {
       const T w = lane < SCAN_WARPS ? s_warp[lane] : T(0);
       const T wi = warp_incl_scan(w, lane);
-      woff = shfl_idx((T)(wi - w), warp);
+      woff = ::kb200::Impl::shfl_idx((T)(wi - w), warp);
     }
     {
       KB200_CS_T0();

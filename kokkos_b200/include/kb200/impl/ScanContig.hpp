@@ -115,14 +115,14 @@ KB200_DEVICE_FUNCTION void scan_counter_release(unsigned long long* counter) {
 template <class T>
 KB200_DEVICE_FUNCTION T warp_sum_all(T v) {
 #pragma unroll
-  for (int m = 16; m > 0; m >>= 1) v += shfl_xor(v, m);
+  for (int m = 16; m > 0; m >>= 1) v += ::kb200::Impl::shfl_xor(v, m);
   return v;
 }
 template <class T>
 KB200_DEVICE_FUNCTION T warp_incl_scan(T v, int lane) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    T u = shfl_up(v, d);
+    T u = ::kb200::Impl::shfl_up(v, d);
     if (lane >= d) v += u;
   }
   return v;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(BLOCK) contig_scan_kernel(const ScanContigPara
       const T w = lane < NWARPS ? s_warp[lane] : T(0);
       const T wi = warp_incl_scan(w, lane);
       if (lane < NWARPS) s_warp[lane] = wi - w;  // exclusive warp offsets
-      const T agg = shfl_idx(wi, NWARPS - 1);
+      const T agg = ::kb200::Impl::shfl_idx(wi, NWARPS - 1);
       ScanDesc16* const d = p.desc + cur;
       T excl = T(0);
       if (cur == 0) {
@@ -386,7 +386,7 @@ KB200_DEVICE_FUNCTION void round_publish(const ScanContigParams<T>& p, int64 kk,
         const unsigned bal = __ballot_sync(kFullMask, have);
         if (bal) {
           m = __ffs(bal) - 1;
-          rbm = shfl_idx(v, m);
+          rbm = ::kb200::Impl::shfl_idx(v, m);
           break;
         }
         if ((spin & 1023u) == 1023u) {
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(CBLOCK + 96 + (ROUNDS ? 32 : 0)) contig_scan_w
               ll::st_gpu(acc, 0ull, 0ull);
             }
             const unsigned long long bits = (w0 & 0xffffffffffffull) + ((w1 & 0xffffffffffffull) << 32);
-            own_prev = shfl_idx(from_bits<T>(bits), 0);
+            own_prev = ::kb200::Impl::shfl_idx(from_bits<T>(bits), 0);
             if (lane < p.world) {
               unsigned long long a0, a1;
               ll::pack(own_prev, p.rtag_base + (unsigned)k1, a0, a1);
@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(CBLOCK + 96 + (ROUNDS ? 32 : 0)) contig_scan_w
     {
       const T w = lane < NWARPS ? s_warp[lane] : T(0);
       const T wi = warp_incl_scan(w, lane);
-      woff = shfl_idx((T)(wi - w), warp);
+      woff = ::kb200::Impl::shfl_idx((T)(wi - w), warp);
     }
 #ifdef B200_SWEEP
     const long long t_w1 = clock64();
@@ -829,7 +829,8 @@ struct ContigScanLaunch {
   }
   static auto rounds_kernel() { return contig_scan_ws2_kernel<T, BLOCK, NV, NBUF, LBW, INCLUSIVE, true>; }
   static int resident_blocks_per_sm() {
-    static int cached = 0;
+    static PerDeviceInt cache;  // the shared-memory opt-in below is per device
+    int& cached = cache.here();
     if (cached == 0) {
       auto k = kernel();
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
@@ -854,7 +855,8 @@ struct ContigScanLaunch {
       }
       return 0;
     }
-    static int bps_cached = 0;
+    static PerDeviceInt cache;
+    int& bps_cached = cache.here();
     if (bps_cached == 0) {
       auto k = rounds_kernel();
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(CBLOCK + 32) contig_scan_ws_kernel(const ScanC
       const T w = lane < NWARPS ? s_warp[lane] : T(0);
       const T wi = warp_incl_scan(w, lane);
       if (lane < NWARPS) s_warp[lane] = wi - w;
-      const T agg = shfl_idx(wi, NWARPS - 1);
+      const T agg = ::kb200::Impl::shfl_idx(wi, NWARPS - 1);
       ScanDesc16* const d = p.desc + cur;
       T excl = T(0);
       if (cur == 0) {
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(CBLOCK + 128) contig_scan_ws3_kernel(const Sca
     {
       const T w = lane < NWARPS ? s_warp[lane] : T(0);
       const T wi = warp_incl_scan(w, lane);
-      woff = shfl_idx((T)(wi - w), warp);
+      woff = ::kb200::Impl::shfl_idx((T)(wi - w), warp);
     }
 #ifdef B200_SWEEP
     const long long t_w1 = clock64();
@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(CBLOCK + 96 + 32 * NSTAGE) contig_scan_ws4_ker
     {
       const T w = lane < NWARPS ? s_warp[lane] : T(0);
       const T wi = warp_incl_scan(w, lane);
-      woff = shfl_idx((T)(wi - w), warp);
+      woff = ::kb200::Impl::shfl_idx((T)(wi - w), warp);
     }
 #ifdef B200_SWEEP
     const long long t_w1 = clock64();

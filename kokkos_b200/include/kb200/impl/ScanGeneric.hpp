@@ -49,7 +49,7 @@ KB200_DEVICE_FUNCTION void warp_incl_scan_ordered(const Red& red, typename Red::
   using V = typename Red::value_type;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    V lo = shfl_up(v, d);
+    V lo = ::kb200::Impl::shfl_up(v, d);
     if (lane >= d) { red.join(lo, v); v = lo; }
   }
 }
@@ -85,10 +85,10 @@ KB200_DEVICE_FUNCTION typename Red::value_type lookback_ordered(const Red& red, 
     // fold lanes first_term .. 0 (older tile = higher lane = LEFT operand)
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      V hi = shfl_down(val, d);
+      V hi = ::kb200::Impl::shfl_down(val, d);
       if (lane + d < 32) { red.join(hi, val); val = hi; }
     }
-    V window = shfl_idx(val, 0);
+    V window = ::kb200::Impl::shfl_idx(val, 0);
     if (have) { red.join(window, excl); }
     excl = window;
     have = true;
@@ -125,10 +125,10 @@ KB200_DEVICE_FUNCTION typename Red::value_type lookback_ordered_packed(const Red
     if (lane > first_term) red.init(val);
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      V hi = shfl_down(val, d);
+      V hi = ::kb200::Impl::shfl_down(val, d);
       if (lane + d < 32) { red.join(hi, val); val = hi; }
     }
-    V window = shfl_idx(val, 0);
+    V window = ::kb200::Impl::shfl_idx(val, 0);
     if (have) { red.join(window, excl); }
     excl = window;
     have = true;
@@ -256,10 +256,10 @@ __global__ void __launch_bounds__(BLOCK)
       if (lane < NWARPS) w = s_warp[lane];
       V wi = w;
       warp_incl_scan_ordered(red, wi, lane);
-      V wex = shfl_up(wi, 1);  // exclusive warp prefix
+      V wex = ::kb200::Impl::shfl_up(wi, 1);  // exclusive warp prefix
       if (lane == 0) red.init(wex);
       if (lane < NWARPS) s_warp[lane] = wex;
-      V agg = shfl_idx(wi, NWARPS - 1);
+      V agg = ::kb200::Impl::shfl_idx(wi, NWARPS - 1);
       if (lane == 0) {
         *s_agg = agg;
         const unsigned long long state = tile == 0 ? 2ull : 1ull;  // tile 0: its aggregate IS its inclusive prefix
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(BLOCK)
     __syncthreads();
     {  // tile-local exclusive prefix of every element, blocked write-back (the tile prefix is joined in step (2) next time)
       V run = s_warp[warp];
-      V tex = shfl_up(tincl, 1);  // exclusive thread prefix inside the warp
+      V tex = ::kb200::Impl::shfl_up(tincl, 1);  // exclusive thread prefix inside the warp
       if (lane != 0) red.join(run, tex);
 #pragma unroll
       for (int k = 0; k < ITEMS; ++k) {
@@ -314,7 +314,8 @@ struct GenericScan {
       return 0;
     }
     auto k = generic_scan_kernel<F, Tag, Index, Red, BLOCK, ITEMS>;
-    static int bps = 0;
+    static PerDeviceInt cache;  // the shared-memory opt-in below is per device
+    int& bps = cache.here();
     if (bps == 0) {
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, BLOCK, SMEM);

@@ -103,6 +103,15 @@ class ShardedB200:
         buffers live (the GPU for NCCL, CPU for gloo)."""
         self.local = local
         self.group = group
+        # Stream order: the local kernels run on the instance's stream, torch.distributed collectives and `.cpu()` on torch's
+        # CURRENT stream.  Nothing else orders them, so the two must be the same stream (build the instance with
+        # kb.B200(device, stream=torch.cuda.current_stream().cuda_stream), as bench.py does).
+        if (dist.is_available() and dist.is_initialized() and torch.cuda.is_available() and getattr(local, "stream", None)
+                and coll_device is not None and torch.device(coll_device).type == "cuda"):
+            cur = torch.cuda.current_stream(torch.device(coll_device)).cuda_stream
+            if int(local.stream) != int(cur):
+                raise ValueError("ShardedB200: the execution-space instance must be created on torch's current CUDA stream "
+                                 "(its kernels and the collectives are ordered by that stream only)")
         if dist.is_available() and dist.is_initialized():
             self.rank = dist.get_rank(group)
             self.world = dist.get_world_size(group)
