@@ -301,6 +301,10 @@ class B200:
         _check(self.lib.b200_reduce_minmaxloc_f64(self.handle, v.ptr, v.n, index_base, byref(out), None))
         return out
 
+    def parallel_reduce_minmaxloc_dev(self, v: View, index_base: int, result_dev: int) -> None:
+        """Asynchronous form: the 32-byte b200_minmaxloc_f64 goes to device memory at `result_dev`."""
+        _check(self.lib.b200_reduce_minmaxloc_f64(self.handle, v.ptr, v.n, index_base, None, result_dev))
+
     # ---- parallel_scan ----
     def parallel_scan(self, x: View, y: View, inclusive: bool = False, seed=0, total_dev: int = 0, blocking: bool = True):
         if x.dtype != y.dtype or x.n != y.n:
@@ -357,6 +361,12 @@ class B200:
         _check(self.lib.b200_stencil7_minmaxloc_f64(self.handle, u.ptr, v_out.ptr if v_out else None, n0, n1, n2, c0, c1,
                                                     byref(out), None))
         return out
+
+    def stencil7_minmaxloc_dev(self, u: View, n0: int, n1: int, n2: int, c0: float, c1: float, result_dev: int, v_out: View | None = None) -> None:
+        """Asynchronous form: the 32-byte b200_minmaxloc_f64 goes to device memory at `result_dev`."""
+        if u.n != n0 * n1 * n2:
+            raise B200Error(-1, "stencil7: extent mismatch")
+        _check(self.lib.b200_stencil7_minmaxloc_f64(self.handle, u.ptr, v_out.ptr if v_out else None, n0, n1, n2, c0, c1, None, result_dev))
 
     # ---- atomics ----
     def gups(self, table: View, indices: View, datum: int, op: str = "add") -> None:

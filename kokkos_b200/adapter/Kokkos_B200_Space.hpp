@@ -56,7 +56,9 @@ class B200 {
 
   B200() : m_space() {}  // the default instance (created by Kokkos::initialize through the space factory)
   explicit B200(cudaStream_t stream) : m_space(stream) {}
-  explicit B200(const kb200::B200& s) : m_space(s) {}
+  // deduced parameter: a braced list ({{0, 0}} in MDRangePolicy calls) must never be tried as an execution space
+  template <class S, std::enable_if_t<std::is_same_v<S, kb200::B200>, int> = 0>
+  explicit B200(const S& s) : m_space(s) {}
 
   static void impl_initialize(InitializationSettings const& settings) {
     int device = 0;
@@ -141,6 +143,11 @@ struct ZeroMemset<Kokkos::B200> {
 };
 
 namespace B200Adapter {
+// What the reference's Cuda launch path does before every kernel (Cuda/Kokkos_Cuda_KernelLaunch.hpp:693): without relocatable
+// device code each translation unit has its own copy of desul's lock-array pointers (the fallback for atomics on types wider
+// than 8 bytes, e.g. Kokkos::complex<double>); user functors run on this space may use them too.
+inline void before_launch() { desul::ensure_cuda_lock_arrays_on_device(); }
+
 // ---- policy translation -------------------------------------------------------------------------------------------
 template <class S>
 struct schedule_of { using type = kb200::Schedule<kb200::Static>; };
@@ -209,7 +216,8 @@ class ParallelFor<FunctorType, Kokkos::RangePolicy<Traits...>, Kokkos::B200> {
 
   ParallelFor(const FunctorType& arg_functor, const Policy& arg_policy) : m_functor(arg_functor), m_policy(arg_policy) {}
   Policy const& get_policy() const { return m_policy; }
-  void execute() const { kb200::parallel_for(B200Adapter::to_kb(m_policy), m_functor); }
+  void execute() const {
+    B200Adapter::before_launch(); kb200::parallel_for(B200Adapter::to_kb(m_policy), m_functor); }
 
  private:
   const FunctorType m_functor;
@@ -236,6 +244,7 @@ class ParallelReduce<CombinedFunctorReducerType, Kokkos::RangePolicy<Traits...>,
   Policy const& get_policy() const { return m_policy; }
 
   void execute() const {
+    B200Adapter::before_launch();
     value_type* const host = m_result_ptr_device_accessible ? nullptr : (value_type*)m_result_ptr;
     value_type* const dev  = m_result_ptr_device_accessible ? (value_type*)m_result_ptr : nullptr;
     if constexpr (B200Adapter::is_array_reduction<ReducerType>) {
@@ -266,6 +275,7 @@ class ParallelScan<FunctorType, Kokkos::RangePolicy<Traits...>, Kokkos::B200> {
   ParallelScan(const FunctorType& arg_functor, const Policy& arg_policy) : m_functor(arg_functor), m_policy(arg_policy) {}
   Policy const& get_policy() const { return m_policy; }
   void execute() const {
+    B200Adapter::before_launch();
     using KP  = B200Adapter::kb_range_policy<Policy>;
     using Red = kb200::Impl::FunctorReducer<FunctorType, value_type, typename Policy::work_tag>;
     kb200::Impl::throw_on_error(
@@ -293,6 +303,7 @@ class ParallelScanWithTotal<FunctorType, Kokkos::RangePolicy<Traits...>, ReturnT
         m_result_ptr_device_accessible(MemorySpaceAccess<Kokkos::CudaSpace, typename ViewType::memory_space>::accessible) {}
   Policy const& get_policy() const { return m_policy; }
   void execute() const {
+    B200Adapter::before_launch();
     using KP  = B200Adapter::kb_range_policy<Policy>;
     using Red = kb200::Impl::FunctorReducer<FunctorType, value_type, typename Policy::work_tag>;
     value_type* const host = m_result_ptr_device_accessible ? nullptr : (value_type*)m_result_ptr;
@@ -318,7 +329,8 @@ class ParallelFor<FunctorType, Kokkos::MDRangePolicy<Traits...>, Kokkos::B200> {
   Policy const& get_policy() const { return m_policy; }
   template <typename P, typename F>
   static int max_tile_size_product(const P&, const F&) { return 1024; }
-  void execute() const { kb200::parallel_for(B200Adapter::to_kb_md(m_policy), m_functor); }
+  void execute() const {
+    B200Adapter::before_launch(); kb200::parallel_for(B200Adapter::to_kb_md(m_policy), m_functor); }
 
  private:
   const FunctorType m_functor;
@@ -347,6 +359,7 @@ class ParallelReduce<CombinedFunctorReducerType, Kokkos::MDRangePolicy<Traits...
   static int max_tile_size_product(const P&, const F&) { return 512; }
 
   void execute() const {
+    B200Adapter::before_launch();
     value_type* const host = m_result_ptr_device_accessible ? nullptr : (value_type*)m_result_ptr;
     value_type* const dev  = m_result_ptr_device_accessible ? (value_type*)m_result_ptr : nullptr;
     if constexpr (B200Adapter::is_array_reduction<ReducerType>) {

@@ -192,9 +192,18 @@ int TeamPolicyInternal<Kokkos::B200, Properties...>::team_size_max(const Functor
 template <class... Properties>
 template <class FunctorType>
 int TeamPolicyInternal<Kokkos::B200, Properties...>::team_size_max(const FunctorType& f, const ParallelReduceTag&) const {
-  // the value type is only known with the result argument: bound by the for-kernel of the same functor, halved (as kb200 does)
-  const int mx = impl_to_kb().team_size_max(B200Adapter::TeamNullWrap<FunctorType>{f}, kb200::ParallelForTag());
-  return mx > 1 ? mx / 2 : 1;
+  // the reference's own analysis names the value type and reducer a result-less call would use (model:
+  // Cuda/Kokkos_Cuda_Parallel_Team.hpp:111-128); the bound then comes from the reduction kernel that would be launched
+  using Analysis = Impl::FunctorAnalysis<Impl::FunctorPatternInterface::REDUCE, TeamPolicyInternal, FunctorType, void>;
+  if constexpr (Analysis::StaticValueSize != 0) {
+    using V = typename Analysis::value_type;
+    using W = B200Adapter::TeamReduceWrap<FunctorType, typename traits::work_tag, V>;
+    using R = B200Adapter::Red<typename Analysis::Reducer>;
+    return kb200::Impl::team_size_limit_reduce<R>(impl_to_kb(), W{f});
+  } else {  // runtime-length array value: bound by the for-kernel of the same functor, halved
+    const int mx = impl_to_kb().team_size_max(B200Adapter::TeamNullWrap<FunctorType>{f}, kb200::ParallelForTag());
+    return mx > 1 ? mx / 2 : 1;
+  }
 }
 
 template <class FunctorType, class... Properties>
@@ -205,6 +214,7 @@ class ParallelFor<FunctorType, Kokkos::TeamPolicy<Properties...>, Kokkos::B200> 
   ParallelFor(const FunctorType& arg_functor, const Policy& arg_policy) : m_functor(arg_functor), m_policy(arg_policy) {}
   Policy const& get_policy() const { return m_policy; }
   void execute() const {
+    B200Adapter::before_launch();
     using W = B200Adapter::TeamForWrap<FunctorType, typename Policy::work_tag>;
     kb200::parallel_for(m_policy.impl_to_kb(), W{m_functor});
   }
@@ -234,6 +244,7 @@ class ParallelReduce<CombinedFunctorReducerType, Kokkos::TeamPolicy<Properties..
   Policy const& get_policy() const { return m_policy; }
 
   void execute() const {
+    B200Adapter::before_launch();
     value_type* const host = m_result_ptr_device_accessible ? nullptr : (value_type*)m_result_ptr;
     value_type* const dev  = m_result_ptr_device_accessible ? (value_type*)m_result_ptr : nullptr;
     if constexpr (B200Adapter::is_array_reduction<ReducerType>) {

@@ -611,10 +611,40 @@ template <class F> struct team_reduce_value_known<F, std::void_t<typename team_r
 template <class F, bool = team_reduce_value_known<F>::value> struct team_reduce_scalar_value_known : std::false_type {};
 template <class F> struct team_reduce_scalar_value_known<F, true> : std::integral_constant<bool, !std::is_array<typename team_reduce_value_of<F>::type>::value> {};
 
+// team size bound from the attributes of the kernel that would be launched and the level-0 scratch request
+template <class Policy, class F>
+int team_size_from_attr(const Policy& pol, const F& f, const cudaFuncAttributes& attr, size_t value_bytes, bool halve) {
+  const int vec = pol.impl_vector_length() > 0 ? pol.impl_vector_length() : 1;
+  int max_threads = attr.maxThreadsPerBlock > 0 ? attr.maxThreadsPerBlock : 1024;
+  if (halve) max_threads /= 2;
+  constexpr unsigned lb = Policy::launch_bounds::maxTperB;
+  if (lb > 0 && (int)lb < max_threads) max_threads = (int)lb;
+  int team = max_threads / vec;
+  // level-0 scratch (policy request + what the functor asks for itself) must fit next to the collective area
+  while (team > 1) {
+    size_t coll = kTeamCollectiveBytes;
+    if (value_bytes * 34 > coll) coll = value_bytes * 34;
+    const size_t l0 = pol.team_scratch_size(0) + TeamShape<Policy>::functor_shmem(f, team) + pol.thread_scratch_size(0) * (size_t)team;
+    if (coll + l0 + 16 <= (size_t)220 * 1024) break;
+    team /= 2;
+  }
+  if (team * vec >= 32) team = (team * vec / 32) * 32 / vec;  // whole warps
+  return team > 0 ? team : 1;
+}
+
+// the reduction kernel is known exactly (functor wrapper + reducer type): used by the Kokkos::B200 adapter, where the reference's
+// FunctorAnalysis supplies the reducer
+template <class Red, class Policy, class F>
+int team_size_limit_reduce(const Policy& pol, const F& f) {
+  using Tag = typename Policy::work_tag;
+  cudaFuncAttributes attr{};
+  throw_on_error(b200_report_error((int)cudaFuncGetAttributes(&attr, team_reduce_kernel<F, Tag, Red>), "kb200::team_size_max"));
+  return team_size_from_attr(pol, f, attr, sizeof(typename Red::value_type), false);
+}
+
 template <class Policy, class F, class PatternTag>
 int team_size_limit(const Policy& pol, const F& f, const PatternTag&) {
   using Tag = typename Policy::work_tag;
-  const int vec = pol.impl_vector_length() > 0 ? pol.impl_vector_length() : 1;
   cudaFuncAttributes attr{};
   size_t value_bytes = 16;
   bool halve = false;
@@ -631,21 +661,7 @@ int team_size_limit(const Policy& pol, const F& f, const PatternTag&) {
   } else {
     throw_on_error(b200_report_error((int)cudaFuncGetAttributes(&attr, team_for_kernel<F, Tag>), "kb200::team_size_max"));
   }
-  int max_threads = attr.maxThreadsPerBlock > 0 ? attr.maxThreadsPerBlock : 1024;
-  if (halve) max_threads /= 2;
-  constexpr unsigned lb = Policy::launch_bounds::maxTperB;
-  if (lb > 0 && (int)lb < max_threads) max_threads = (int)lb;
-  int team = max_threads / vec;
-  // level-0 scratch (policy request + what the functor asks for itself) must fit next to the collective area
-  while (team > 1) {
-    size_t coll = kTeamCollectiveBytes;
-    if (value_bytes * 34 > coll) coll = value_bytes * 34;
-    const size_t l0 = pol.team_scratch_size(0) + TeamShape<Policy>::functor_shmem(f, team) + pol.thread_scratch_size(0) * (size_t)team;
-    if (coll + l0 + 16 <= (size_t)220 * 1024) break;
-    team /= 2;
-  }
-  if (team * vec >= 32) team = (team * vec / 32) * 32 / vec;  // whole warps
-  return team > 0 ? team : 1;
+  return team_size_from_attr(pol, f, attr, value_bytes, halve);
 }
 }  // namespace Impl
 

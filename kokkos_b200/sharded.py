@@ -11,9 +11,14 @@ GPU, ``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the CPU tes
                                                                RANK ORDER with the reference's join rule
                                                                (core/src/Kokkos_Parallel_Reduce.hpp:441-449,628-644), so
                                                                equal extrema keep the lowest-ranked (= lowest index) location
-  parallel_scan                                                local total -> all_gather (8 B per rank) -> the seeded local
+  parallel_scan  (contiguous shards)                           local total -> all_gather (8 B per rank) -> the seeded local
                                                                scan sums the lower ranks' totals itself on the device
                                                                (b200_scan_excl_i64_seeds_dev): reduce-then-scan, 24 B/element
+  parallel_scan  (block-cyclic shards, needs `comm`)           ONE fused kernel per rank (b200_comm_scan_*): round aggregates
+                                                               travel over peer-mapped NVLink mailboxes, 16 B/element at any N
+
+With `comm` (kokkos_b200.Comm, the library's own one-box communicator) the few-byte combines run as device-side,
+stream-ordered kernels of this library (no host round trip); without it they go through torch.distributed.
 
 The local work is done by a *local executor*: on a GPU box that is always ``kokkos_b200.B200`` (there is no CPU
 fallback in this package); the world_size-2 gloo tests inject a stand-in built on the test oracle to exercise the
@@ -97,12 +102,13 @@ class MinMaxLocResult:
 class ShardedB200:
     """Rank-local handle of a range-sharded execution over `world` B200s (one process per GPU)."""
 
-    def __init__(self, local, group=None, coll_device=None):
+    def __init__(self, local, group=None, coll_device=None, comm=None):
         """`local`: the rank's execution-space instance (kokkos_b200.B200).  `group`: torch.distributed process group
         (default: WORLD; None with no initialised backend = single GPU).  `coll_device`: where the few-byte collective
-        buffers live (the GPU for NCCL, CPU for gloo)."""
+        buffers live (the GPU for NCCL, CPU for gloo).  `comm`: optional kokkos_b200.Comm over the same ranks."""
         self.local = local
         self.group = group
+        self.comm = comm
         # Stream order: the local kernels run on the instance's stream, torch.distributed collectives and `.cpu()` on torch's
         # CURRENT stream.  Nothing else orders them, so the two must be the same stream (build the instance with
         # kb.B200(device, stream=torch.cuda.current_stream().cuda_stream), as bench.py does).
@@ -261,3 +267,60 @@ class ShardedB200:
     def barrier(self) -> None:
         if self.world > 1:
             dist.barrier(group=self.group)
+
+    # ------------------------------------------------------------------ device-resident (asynchronous) forms
+    def minmaxloc_async(self, view, index_base: int, out: torch.Tensor) -> torch.Tensor:
+        """MinMaxLoc over a contiguous-sharded View<double*>: the local kernel writes {min_val, max_val, min_loc, max_loc}
+        (32 bytes; `out` = 4-element float64 tensor, the locations are int64 bit patterns) and the rank partials are joined
+        on the device in rank order, lowest location on ties (b200_allreduce_minmaxloc_f64).  Needs `comm` when world > 1."""
+        self.local.parallel_reduce_minmaxloc_dev(view, index_base, out.data_ptr())
+        if self.world > 1:
+            self._need_comm("minmaxloc_async")
+            self.comm.allreduce_loc("minmaxloc", out.data_ptr())
+        return out
+
+    def stencil7_minmaxloc_async(self, u_slab, n0: int, n1: int, n2_local: int, n2_global: int, k_offset: int, c0: float, c1: float,
+                                 out: torch.Tensor) -> torch.Tensor:
+        """Asynchronous k-slab form of stencil7_minmaxloc: result and re-basing stay on the device (`out`: 4 x float64 as above)."""
+        self.local.stencil7_minmaxloc_dev(u_slab, n0, n1, n2_local, c0, c1, out.data_ptr())
+        if self.world > 1 or n2_local != n2_global or k_offset:
+            loc = out[2:4].view(torch.int64)
+            ident = loc == INDEX_IDENTITY
+            reb = torch.div(loc, n2_local, rounding_mode="floor") * n2_global + loc % n2_local + k_offset
+            loc.copy_(torch.where(ident, loc, reb))
+        if self.world > 1:
+            self._need_comm("stencil7_minmaxloc_async")
+            self.comm.allreduce_loc("minmaxloc", out.data_ptr())
+        return out
+
+    def cyclic_scan_async(self, x_local, y_local, n_global: int, total_out: torch.Tensor, inclusive: bool = False) -> None:
+        """Fused distributed parallel_scan over block-cyclic Views (see cyclic_blocks): one kernel per rank, 16 B/element."""
+        if self.world == 1 and self.comm is None:
+            self.local.parallel_scan(x_local, y_local, inclusive=inclusive, total_dev=total_out.data_ptr(), blocking=False)
+            return
+        self._need_comm("cyclic_scan_async")
+        self.comm.parallel_scan(x_local, y_local, n_global, inclusive=inclusive, total_dev=total_out.data_ptr(), blocking=False)
+
+    def _need_comm(self, what: str) -> None:
+        if self.comm is None:
+            raise ValueError(f"ShardedB200.{what}: world > 1 needs the library communicator (pass comm=kokkos_b200.Comm(...))")
+
+    # ------------------------------------------------------------------ parallel_for: shard-local, no exchange
+    def stream_copy(self, a, c) -> None:
+        """benchmarks/stream copy on this rank's shard: c = a (no exchange; stream-kokkos.cpp:217-222)."""
+        self.local.stream_copy(a, c)
+
+    def stream_triad(self, a, b, c, scalar: float) -> None:
+        """benchmarks/stream triad on this rank's shard: a = b + scalar * c (stream-kokkos.cpp:226-231)."""
+        self.local.stream_triad(a, b, c, scalar)
+
+    def gups(self, table_shard, indices_local, datum: int, op: str = "add") -> None:
+        """GUPS on a table sharded by index range: this rank owns table[rank*L, (rank+1)*L) and applies the updates whose
+        targets fall in its shard (`indices_local` are shard-relative).  The update stream is generated per owner (see
+        gups_owner_indices), so no update crosses ranks: weak scaling with no exchange (benchmarks/gups/gups-kokkos.cpp)."""
+        self.local.gups(table_shard, indices_local, datum, op)
+
+    def spmv_rows(self, row_map_local, col_idx, values, x_full, y_local) -> None:
+        """CRS SpMV sharded by rows: this rank holds rows [r0, r1) (row_map re-based to 0) and a full copy of x; y stays
+        shard-local (no exchange)."""
+        self.local.spmv_crs(row_map_local, col_idx, values, x_full, y_local)

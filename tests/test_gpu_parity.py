@@ -174,7 +174,7 @@ def test_scan_closed_form_tile_edges_inplace_and_unaligned(space, n):
 def test_scan_uniform_kernel_on_aligned_views(space, port):
     """The non-warp-specialised kernel normally serves unaligned Views only; force it on aligned ones too."""
     import kokkos_b200 as kb
-    for ws in (0, 1):
+    for ws in (0,):  # ws 1/3/4 are sweep-build variants (kb200/impl/ScanContigSweep.hpp)
       kb.tune_set("scan.ws", ws); kb.tune_set("scan.block", 256); kb.tune_set("scan.nbuf", 2); kb.tune_set("scan.lbw", 2)
       try:
         for n in (4608, 100003, 1 << 20):
