@@ -180,6 +180,9 @@ class Bench:
         # the stream our kernels, the NCCL calls and the timing events share
         self.side = torch.cuda.Stream(device=self.dev)
         torch.cuda.set_stream(self.side)
+        for kv in os.environ.get("KB200_TUNE", "").split(","):  # probe knobs, e.g. KB200_TUNE=for.bps=0,comm.tpr=256
+            if "=" in kv:
+                kb.tune_set(kv.split("=")[0], int(kv.split("=")[1]))
         self.space = kb.B200(self.local_rank, stream=self.side.cuda_stream)
         self.comm = None
         if self.distributed:
@@ -317,16 +320,43 @@ class Bench:
         sp = self.sp
         scan_ev = []
 
+        overlap = self.args.overlap
+        if overlap:
+            # two execution-space instances (as a Kokkos program would use two Kokkos::Cuda instances): the reduce and its
+            # all-reduce run on stream B while the scan runs on the main stream; every step forks and joins with events
+            self.streamB = torch.cuda.Stream(device=self.dev)
+            with torch.cuda.stream(self.streamB):
+                self.spaceB = self.kb.B200(self.local_rank, stream=self.streamB.cuda_stream)
+                from kokkos_b200.sharded import ShardedB200
+                spB = ShardedB200(self.spaceB, coll_device=self.dev)
+                vxdB = self.spaceB.wrap(self.xd.data_ptr(), self.n, self.np.float64)
+            ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+
         def step(record=False):
-            # parallel_reduce Sum<double>: result stays on the device (View result => asynchronous); N>1: + NCCL all-reduce
-            sp.reduce_sum_async(self.vxd, out=self.red_dev)
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(self.side)
-            # parallel_scan: one kernel per rank (N>1: the fused block-cyclic scan over NVLink mailboxes)
-            sp.cyclic_scan_async(self.vxi, self.vyi, self.n_global, self.tot_dev)
+            if overlap:
+                ev_fork.record(self.side)
+                self.streamB.wait_event(ev_fork)
+                if record:
+                    e0.record(self.side)
+                sp.cyclic_scan_async(self.vxi, self.vyi, self.n_global, self.tot_dev)   # launched first: it needs the shared memory
+                if record:
+                    e1.record(self.side)
+                with torch.cuda.stream(self.streamB):
+                    spB.reduce_sum_async(vxdB, out=self.red_dev)
+                    ev_join.record(self.streamB)
+                self.side.wait_event(ev_join)
+            else:
+                # parallel_reduce Sum<double>: result stays on the device (View result => asynchronous); N>1: + NCCL all-reduce
+                sp.reduce_sum_async(self.vxd, out=self.red_dev)
+                if record:
+                    e0.record(self.side)
+                # parallel_scan: one kernel per rank (N>1: the fused block-cyclic scan over NVLink mailboxes)
+                sp.cyclic_scan_async(self.vxi, self.vyi, self.n_global, self.tot_dev)
+                if record:
+                    e1.record(self.side)
             if record:
-                e1.record(self.side)
                 scan_ev.append((e0, e1))
 
         for _ in range(self.warmup):
@@ -353,7 +383,12 @@ class Bench:
         self.sync_all()
         self.clocks = sampler.stop()
         self.ms_per_step = self.max_over_ranks(t0.elapsed_time(t1)) / self.steps
-        self.scan_ms = self.max_over_ranks(sum(a.elapsed_time(b) for a, b in scan_ev) / len(scan_ev))
+        self.scan_ms_in_step = self.max_over_ranks(sum(a.elapsed_time(b) for a, b in scan_ev) / len(scan_ev))
+        self.scan_ms = self.scan_ms_in_step
+        if overlap:
+            # the dominant kernel timed ALONE (inside a step it shares the machine with the reduce): same launches, same data
+            self.scan_ms = self.timed(lambda: sp.cyclic_scan_async(self.vxi, self.vyi, self.n_global, self.tot_dev), warmup=1)
+            self.reduce_ms_alone = self.timed(lambda: sp.reduce_sum_async(self.vxd, out=self.red_dev), warmup=1)
         self.bytes_per_step = 24.0 * self.n * self.world
         self.value = self.bytes_per_step / (self.ms_per_step * 1e-3) / 1e9
         self.launches_per_step = 2  # range_reduce_kernel + contig_scan_ws2_kernel (plain at N=1, rounds form at N>1)
@@ -368,7 +403,9 @@ class Bench:
         kname = "contig_scan_ws2_kernel<int64,128,9,4,1> (single-pass look-back scan" + (", ROUNDS form: block-cyclic over NVLink mailboxes)" if self.distributed else ")")
         return {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": self.peak, "unit": "GB/s", "frac": achieved / self.peak,
                 "traffic": traffic if not self.distributed else None, "peak_source": self.peak_src,
-                "algorithmic_bytes_per_launch": 16.0 * self.n_local, "avg_launch_ms": self.scan_ms, "frac_of_8TBs_nominal": achieved / 8000.0}
+                "algorithmic_bytes_per_launch": 16.0 * self.n_local, "avg_launch_ms": self.scan_ms, "frac_of_8TBs_nominal": achieved / 8000.0,
+                "timing": ("kernel timed alone, %d launches with CUDA events right after the timed steps (inside a step it runs concurrently with the "
+                           "reduce kernel: %.3f ms there)" % (self.steps, self.scan_ms_in_step)) if self.args.overlap else "CUDA events around each launch inside the timed steps"}
 
     # ---- Kokkos user code on Kokkos::B200 (adapter) and the comparators --------------------------------------------
     def kokkos_api_and_comparators(self):
@@ -404,15 +441,23 @@ class Bench:
             assert torch.equal(y2, ysc), (A.ARM_NAMES[arm], "scan output differs from the typed path")
             if arm != A.CUB:
                 assert int(t.item()) == exp_total, (A.ARM_NAMES[arm], "scan total")
+            y2.fill_(-1)
+            std_ms = self.timed(lambda: self.arms.std_exclusive_scan(arm, xs.data_ptr(), y2.data_ptr(), nl))
+            assert torch.equal(y2, ysc), (A.ARM_NAMES[arm], "std exclusive_scan output differs from the typed path")
             out[arm] = {"reduce_ms": red_ms, "scan_ms": scan_ms, "reduce_GBs": 8.0 * n / red_ms / 1e6, "scan_GBs": 16.0 * nl / scan_ms / 1e6,
-                        "step_GBs_per_gpu": (8.0 * n + 16.0 * nl) / (red_ms + scan_ms) / 1e6}
+                        "step_GBs_per_gpu": (8.0 * n + 16.0 * nl) / (red_ms + scan_ms) / 1e6,
+                        "std_exclusive_scan_ms": std_ms, "std_exclusive_scan_GBs": 16.0 * nl / std_ms / 1e6,
+                        "step_GBs_per_gpu_with_std_exclusive_scan": (8.0 * n + 16.0 * nl) / (red_ms + std_ms) / 1e6}
         del y2, ysc
         api = dict(out[A.B200])
         api["what"] = ("Kokkos::parallel_reduce / Kokkos::parallel_scan with KOKKOS_LAMBDA functors over RangePolicy<Kokkos::B200> on the UNMODIFIED "
-                       "reference headers (kokkos_b200/adapter; benchlib/kokkos_arms.cu), per GPU on its own shard, results bit-identical to the typed path")
+                       "reference headers (kokkos_b200/adapter; benchlib/kokkos_arms.cu), per GPU on its own shard, results bit-identical to the typed path; "
+                       "std_exclusive_scan = Kokkos::Experimental::exclusive_scan(exec, in, out, 0) (blocking: the reference fences), which the adapter "
+                       "routes to the typed look-back kernel the way the reference routes its Cuda inclusive_scan to thrust/CUB")
         comp = {"Kokkos::Cuda (reference backend built for sm_100a, same lambdas)": out[A.CUDA],
                 "CUB DeviceReduce::Sum + DeviceScan::ExclusiveSum (CUDA 12.9 CCCL)": out[A.CUB],
-                "speedup_vs_Kokkos::Cuda": {"reduce": out[A.CUDA]["reduce_ms"] / out[A.B200]["reduce_ms"], "scan": out[A.CUDA]["scan_ms"] / out[A.B200]["scan_ms"]},
+                "speedup_vs_Kokkos::Cuda": {"reduce": out[A.CUDA]["reduce_ms"] / out[A.B200]["reduce_ms"], "scan": out[A.CUDA]["scan_ms"] / out[A.B200]["scan_ms"],
+                                            "std_exclusive_scan": out[A.CUDA]["std_exclusive_scan_ms"] / out[A.B200]["std_exclusive_scan_ms"]},
                 "speedup_vs_CUB": {"reduce": out[A.CUB]["reduce_ms"] / out[A.B200]["reduce_ms"], "scan": out[A.CUB]["scan_ms"] / out[A.B200]["scan_ms"]}}
         return api, comp
 
@@ -596,10 +641,17 @@ class Bench:
             torch.cuda.synchronize(self.dev)
             e2e_steps = max(2, min(self.steps, 3))
 
+            # the two host-buffer calls of a step run on two execution-space instances from two host threads: the scan's
+            # D2H traffic overlaps the reduce's H2D traffic (PCIe is full duplex); each call is blocking, as a scalar-result
+            # parallel_reduce / a parallel_scan followed by deep_copy-to-host is in the reference
+            from concurrent.futures import ThreadPoolExecutor
+            space2 = self.kb.B200(self.local_rank)
+            pool = ThreadPoolExecutor(2)
+
             def e2e_step():
-                r = self.space.parallel_reduce_sum_host(hx.data_ptr(), n)
-                t = self.space.parallel_scan_host(hi.data_ptr(), hy.data_ptr(), nl, 0)
-                return r, t
+                fr = pool.submit(space2.parallel_reduce_sum_host, hx.data_ptr(), n)
+                ft = pool.submit(self.space.parallel_scan_host, hi.data_ptr(), hy.data_ptr(), nl, 0)
+                return fr.result(), ft.result()
             e2e_step()  # warm-up (allocates the staging buffers)
             self.sync_all()
             w0 = time.perf_counter()
@@ -612,7 +664,9 @@ class Bench:
             assert torch.equal(hy[: 1 << 20].to(self.dev), torch.cumsum(xs[: 1 << 20], 0) - xs[: 1 << 20])
             return {"value": (8.0 * n + 16.0 * nl) * self.world / (wall / e2e_steps) / 1e9, "unit": "GB/s",
                     "h2d_bytes_per_step": 8 * n + 8 * nl, "d2h_bytes_per_step": 8 * nl + 16, "steps": e2e_steps,
-                    "api": "b200_reduce_sum_f64_host + b200_scan_excl_i64_host (pinned host buffers, 64 MiB chunks, double-buffered)",
+                    "api": "b200_reduce_sum_f64_host + b200_scan_excl_i64_host (pinned host buffers, 64 MiB chunks, double-buffered), issued from two host "
+                           "threads on two instances so that H2D and D2H overlap",
+                    "pcie_bound_GBs_per_gpu": "24 B of metric per 16 B of H2D: <= 1.5 x the H2D rate (~55 GB/s) = ~83",
                     "note": "per-GPU shards are independent on this leg (no cross-GPU seed): PCIe-bound"}
         except Exception as ex:  # e.g. not enough pinnable host memory
             return {"value": None, "unit": "GB/s", "error": repr(ex)[:200]}
@@ -625,6 +679,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=LOG2N_DEFAULT, help="elements per GPU and per View = 2^log2n")
+    ap.add_argument("--overlap", type=int, default=1, help="1: reduce and scan of a step run concurrently on two execution-space instances; 0: back to back")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the C2/C4/C5 legs")
@@ -665,6 +720,8 @@ def main():
                 "vs_baseline": None, "dtype": "f64+int64", "data": "synthetic",
                 "config": {"workload": workload_text(args.log2n), "policy": "RangePolicy", "elements_per_gpu_per_view": n,
                            "scan_elements_on_rank0": B.n_local, "algorithmic_bytes_per_step_per_gpu": 24 * n, "parallelism": par,
+                           "step": ("the reduce and the scan of a step are issued on two execution-space instances (two streams) and run concurrently; "
+                                    "a step ends when both are done" if args.overlap else "reduce then scan, one stream"),
                            "api": "typed C-ABI entry points (b200_reduce_sum_f64, b200_scan_excl_i64 / b200_comm_scan_excl_i64): the same calls at every N; "
                                   "the Kokkos-lambda form of the same step is `kokkos_api`",
                            "l2": "inputs (8 GiB per View) are far larger than the 126 MB L2; no flush needed",
@@ -673,8 +730,12 @@ def main():
                 "frac_of_measured_peak": B.value / (B.peak * world), "frac_of_8TBs_nominal": B.value / (8000.0 * world),
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": B.launches_per_step * args.steps,
                 "clocks": B.clocks, "kokkos_api": api, "comparators": comp,
-                "breakdown": {"scan_GBs_per_gpu": roofline["achieved"], "reduce_plus_collectives_ms": B.ms_per_step - B.scan_ms, "scan_ms": B.scan_ms,
-                              "reduce_GBs_per_gpu": 8.0 * n / ((B.ms_per_step - B.scan_ms) * 1e-3) / 1e9, "configs": cfgs}}
+                "breakdown": {"scan_GBs_per_gpu": roofline["achieved"], "scan_ms": B.scan_ms, "scan_ms_inside_step": B.scan_ms_in_step,
+                              "reduce_plus_collectives_ms": (B.reduce_ms_alone if args.overlap else B.ms_per_step - B.scan_ms),
+                              "reduce_GBs_per_gpu": 8.0 * n / ((B.reduce_ms_alone if args.overlap else B.ms_per_step - B.scan_ms) * 1e-3) / 1e9,
+                              "step_structure": ("reduce (+ NCCL all-reduce) on instance B || scan on instance A, fork/join by events every step" if args.overlap
+                                                 else "reduce then scan on one instance"),
+                              "configs": cfgs}}
         if getattr(B, "arms_error", None):
             line["arms_error"] = B.arms_error
         print(json.dumps(line), flush=True)

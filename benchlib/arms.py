@@ -29,6 +29,7 @@ class Arms:
         L.kka_init.argtypes = [c_int, c_void_p]
         L.kka_reduce_sum_f64.argtypes = [c_int, c_void_p, c_int64, c_void_p]
         L.kka_scan_excl_i64.argtypes = [c_int, c_void_p, c_void_p, c_int64, c_void_p]
+        L.kka_std_exclusive_scan_i64.argtypes = [c_int, c_void_p, c_void_p, c_int64]
         L.kka_stream_copy_f64.argtypes = [c_int, c_void_p, c_void_p, c_int64]
         L.kka_stream_triad_f64.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_double, c_int64]
         L.kka_stencil7_minmaxloc_f64.argtypes = [c_int, c_void_p, c_int64, c_int64, c_int64, c_double, c_double, c_void_p]
@@ -46,6 +47,9 @@ class Arms:
 
     def scan_excl(self, arm, x_ptr, y_ptr, n, total_dev_ptr):
         self._ok(self.lib.kka_scan_excl_i64(arm, x_ptr, y_ptr, n, total_dev_ptr))
+
+    def std_exclusive_scan(self, arm, x_ptr, y_ptr, n):
+        self._ok(self.lib.kka_std_exclusive_scan_i64(arm, x_ptr, y_ptr, n))
 
     def stream_copy(self, arm, a_ptr, c_ptr, n):
         self._ok(self.lib.kka_stream_copy_f64(arm, a_ptr, c_ptr, n))

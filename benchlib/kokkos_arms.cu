@@ -10,7 +10,7 @@
 // Functors follow the reference's own benchmark sources: benchmarks/stream/stream-kokkos.cpp:217-231 (copy, triad),
 // benchmarks/gups/gups-kokkos.cpp (atomic update loop), core/unit_test/TestReducers.hpp (MinMaxLoc),
 // example/tutorial/Hierarchical_Parallelism (nested TeamThreadRange reduce as CRS SpMV).
-#include <Kokkos_B200_Space.hpp>
+#include <Kokkos_B200_StdAlgorithms.hpp>
 
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
@@ -91,6 +91,14 @@ void scan_excl(const Space& s, const i64* x, i64* y, i64 n, i64* total_dev) {
                         }, t);
 }
 
+// the std_algorithms form of the same prefix sum (blocking: the reference fences at its end)
+template <class Space>
+void std_exclusive_scan(const Space& s, const i64* x, i64* y, i64 n) {
+  DView<const i64> a(x, (size_t)n);
+  DView<i64> b(y, (size_t)n);
+  Kokkos::Experimental::exclusive_scan("arms::std_exclusive_scan", s, a, b, (i64)0);
+}
+
 template <class Space>
 void stream_copy(const Space& s, const double* a_, double* c_, i64 n) {
   DView<const double> a(a_, (size_t)n);
@@ -123,10 +131,12 @@ void stencil7_minmaxloc(const Space& s, const double* u_, i64 n0, i64 n1, i64 n2
                           }, MML(r));
 }
 
+// int64_t (= long on LP64) as in benchmarks/gups: desul has a native red/atom path for it, `long long` would take its CAS loop
 template <class Space>
-void gups_add(const Space& s, i64* table_, i64 table_len, const i64* idx_, i64 m, i64 datum) {
-  DView<i64> table(table_, (size_t)table_len);
-  DView<const i64> idx(idx_, (size_t)m);
+void gups_add(const Space& s, i64* table_, i64 table_len, const i64* idx_, i64 m, i64 datum_) {
+  DView<int64_t> table((int64_t*)table_, (size_t)table_len);
+  DView<const int64_t> idx((const int64_t*)idx_, (size_t)m);
+  const int64_t datum = (int64_t)datum_;
   Kokkos::parallel_for("arms::gups", Kokkos::RangePolicy<Space, Kokkos::IndexType<i64>>(s, 0, m),
                        KOKKOS_LAMBDA(const i64 i) { Kokkos::atomic_add(&table(idx(i)), datum); });
 }
@@ -209,6 +219,11 @@ int kka_scan_excl_i64(int arm, const i64* x, i64* y, i64 n, i64* total_dev) {
     return cub::DeviceScan::ExclusiveSum(g.cub_tmp, need, x, y, n, g.stream) == cudaSuccess ? 0 : -1;
   }
   return dispatch(arm, [&](auto& s) { scan_excl(s, x, y, n, total_dev); });
+}
+// Kokkos::Experimental::exclusive_scan(exec, in, out, 0) (std_algorithms); arm 2 is the same CUB call as above
+int kka_std_exclusive_scan_i64(int arm, const i64* x, i64* y, i64 n) {
+  if (arm == 2) return kka_scan_excl_i64(2, x, y, n, nullptr);
+  return dispatch(arm, [&](auto& s) { std_exclusive_scan(s, x, y, n); });
 }
 int kka_stream_copy_f64(int arm, const double* a, double* c, i64 n) {
   return dispatch(arm, [&](auto& s) { stream_copy(s, a, c, n); });

@@ -17,6 +17,7 @@
 #include "runtime_internal.h"
 #include <kb200/impl/HostRuntime.hpp>
 #include <kb200/impl/Collectives.hpp>
+#include <mutex>
 
 using namespace kb200;
 using namespace kb200::Impl;
@@ -100,26 +101,44 @@ extern "C" int b200_spmv_crs_f64(b200_instance* I, int64_t nrows, const int64_t*
   if (nrows < 0) return b200_set_error(B200_EINVAL, where, "negative row count");
   if (nrows == 0) return 0;
   if (!row_map || !y) return b200_set_error(B200_EINVAL, where, "NULL array");
-  // the vector length is a launch-time choice (TeamPolicy's third argument); the mean row length is
-  // read back once per call -- a View-metadata query in the reference's terms (Crs::numRows / nnz).
-  int64_t ends[2] = {0, 0};
-  cudaError_t e = cudaMemcpyAsync(&ends[0], row_map, 8, cudaMemcpyDeviceToHost, (cudaStream_t)b200_instance_stream(I));
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&ends[1], row_map + nrows, 8, cudaMemcpyDeviceToHost, (cudaStream_t)b200_instance_stream(I));
-  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)b200_instance_stream(I));
-  if (e != cudaSuccess) return b200_set_error((int)e, where, "row_map read-back");
-  const int64 nnz = ends[1] - ends[0];
+  // the vector length is a launch-time choice (TeamPolicy's third argument) made from the mean row length: a View-metadata
+  // query in the reference's terms (Crs::numRows / nnz).  Reading it back costs a stream synchronisation, so the answer is
+  // remembered per (instance, row_map, nrows): repeated products with the same matrix launch without touching the host.
+  // The choice only affects speed -- every vector length is correct for every row length.
+  struct Meta { b200_instance* inst; const int64_t* rm; int64_t nrows, nnz; };
+  static Meta cache[8];
+  static int cache_next = 0;
+  static std::mutex cache_mu;
+  int64 nnz = -1;
+  {
+    std::lock_guard<std::mutex> g(cache_mu);
+    for (const Meta& m : cache) if (m.inst == I && m.rm == row_map && m.nrows == nrows) nnz = m.nnz;
+  }
+  if (nnz < 0) {
+    int64_t ends[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(&ends[0], row_map, 8, cudaMemcpyDeviceToHost, (cudaStream_t)b200_instance_stream(I));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&ends[1], row_map + nrows, 8, cudaMemcpyDeviceToHost, (cudaStream_t)b200_instance_stream(I));
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)b200_instance_stream(I));
+    if (e != cudaSuccess) return b200_set_error((int)e, where, "row_map read-back");
+    nnz = ends[1] - ends[0];
+    std::lock_guard<std::mutex> g(cache_mu);
+    cache[cache_next] = Meta{I, row_map, nrows, nnz};
+    cache_next = (cache_next + 1) % 8;
+  }
   if (nnz > 0 && (!col_idx || !values || !x)) return b200_set_error(B200_EINVAL, where, "NULL array");
   int vl = b200_tune("spmv.vl", 0);
   if (vl == 0) {
     const double mean = (double)nnz / (double)nrows;
-    vl = mean <= 6 ? 4 : mean <= 12 ? 8 : mean <= 64 ? 16 : 32;  // B200 probe (profiles/r01_spmv_probe.log): 16 lanes beat 32 at 32 nnz/row
+    // B200 probe at 32 nnz/row (profiles/r02_spmv_probe.log): 8 lanes 3.80 TB/s, 16 lanes 3.32, 4 lanes 3.24, 32 lanes 2.24 -- about four
+    // nonzeros per lane amortise the shuffle tree best
+    vl = mean <= 6 ? 4 : mean <= 48 ? 8 : mean <= 96 ? 16 : 32;
   }
   const int64* rm = (const int64*)row_map;
   const int ur = b200_tune("spmv.ur", 1);
 #define SPMV_CFG(VL, UR) if (vl == VL && ur == UR) return launch<VL, UR>(I, nrows, rm, col_idx, values, x, y);
-  SPMV_CFG(4, 1) SPMV_CFG(8, 1) SPMV_CFG(16, 1) SPMV_CFG(32, 1)
+  SPMV_CFG(4, 1) SPMV_CFG(8, 1) SPMV_CFG(16, 1) SPMV_CFG(32, 1) SPMV_CFG(8, 2) SPMV_CFG(4, 2)
 #ifdef B200_SWEEP
-  SPMV_CFG(4, 4) SPMV_CFG(8, 4) SPMV_CFG(16, 4) SPMV_CFG(32, 4) SPMV_CFG(32, 2) SPMV_CFG(32, 8) SPMV_CFG(16, 2) SPMV_CFG(16, 8) SPMV_CFG(8, 8) SPMV_CFG(8, 2)
+  SPMV_CFG(4, 4) SPMV_CFG(8, 4) SPMV_CFG(16, 4) SPMV_CFG(32, 4) SPMV_CFG(32, 2) SPMV_CFG(32, 8) SPMV_CFG(16, 2) SPMV_CFG(16, 8) SPMV_CFG(8, 8)
 #endif
 #undef SPMV_CFG
   return b200_set_error(B200_EUNSUPPORTED, where, "vector length must be 4, 8, 16 or 32 (and spmv.ur 4)");

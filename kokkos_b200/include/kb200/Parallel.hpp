@@ -162,12 +162,14 @@ void parallel_for(const std::string& /*label*/, const RangePolicy<P...>& policy,
   // per thread (the reference's mapping) 3.7 TB/s, 256x4 plain 5.59, 256x4 persistent 5.82.
   constexpr bool dynamic = std::is_same<typename Policy::schedule_type, Schedule<Dynamic>>::value;
   using Launch = Impl::RangeForLaunch<Body, 256, 4>;
-  int cap = dynamic ? 0 : 8;
+  static const int static_cap = [] { int v = 8; b200_tune_get("for.bps", &v); return v; }();  // probe knobs, read once
+  static const int waves = [] { int v = 16; b200_tune_get("for.waves", &v); return v; }();
+  int cap = dynamic ? 0 : static_cap;
   if constexpr (Policy::experimental_contains_desired_occupancy) {  // Experimental::prefer(policy, DesiredOccupancy{p})
     cap = policy.impl_occupancy_cap(Launch::resident_blocks_per_sm());
     if (!dynamic && cap > 8) cap = 8;
   }
-  Impl::throw_on_error(Launch::run(policy.space().impl_instance(), body, n, cap));
+  Impl::throw_on_error(Launch::run(policy.space().impl_instance(), body, n, cap, waves));
 }
 template <class... P, class F>
 void parallel_for(const RangePolicy<P...>& policy, const F& f) { parallel_for(std::string(), policy, f); }

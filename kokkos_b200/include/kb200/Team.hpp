@@ -147,9 +147,21 @@ class B200TeamMember {
     return m_scr.impl_set_mode(level, Impl::tm::ny(), Impl::tm::ty());
   }
 
+  // the collective area is sized per launch (Impl::team_collective_bytes): a nested collective on a larger type than it was
+  // sized for must fail loudly, not overwrite level-0 scratch
+  KB200_TEAM_FUNCTION void impl_need_collective(size_t bytes) const {
+    KB200_TEAM_DEVICE_ONLY(
+      if (bytes > (size_t)(m_l0 - (char*)m_collective)) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) printf("kb200: team collective on a value type too large for this launch (%llu bytes needed)\n", (unsigned long long)bytes);
+        __trap();
+      }
+    )
+  }
+
   // ---- team collectives (all threads of the team must call) ----
   template <class T>
   KB200_TEAM_FUNCTION void team_broadcast(T& val, int thread_id) const {
+    impl_need_collective(sizeof(T));
     T* s = reinterpret_cast<T*>(m_collective);
     Impl::tm::sync();
     if (Impl::tm::ty() == thread_id && Impl::tm::tx() == 0) *s = val;
@@ -166,6 +178,7 @@ class B200TeamMember {
   template <class Red>
   KB200_TEAM_FUNCTION void team_reduce(const Red& red, typename Red::value_type& value) const {
     using V = typename Red::value_type;
+    impl_need_collective(32 * sizeof(V));
     V v = value;
     if (Impl::tm::tx() != 0) red.init(v);  // a thread's value counts once, not once per vector lane
     Impl::tm::sync();
@@ -186,7 +199,8 @@ class B200TeamMember {
   // exclusive scan of `value` over team_rank; optional global accumulator gets the team total (Cuda_Team.hpp:249-256)
   template <class T>
   KB200_TEAM_FUNCTION T team_scan(const T& value, T* const global_accum = nullptr) const {
-    T* s = reinterpret_cast<T*>(m_collective);  // team_size + 1 entries fit: collective area is sized for 1024/vl + 2 values of 16 B
+    impl_need_collective((size_t)(Impl::tm::ny() + 1) * sizeof(T));
+    T* s = reinterpret_cast<T*>(m_collective);  // team_size + 1 entries: the area holds team_size + 2 values of 16 B
     Impl::tm::sync();
     if (Impl::tm::tx() == 0) s[Impl::tm::ty() + 1] = value;
     if (Impl::tm::tx() == 0 && Impl::tm::ty() == 0) s[0] = T();
@@ -501,10 +515,20 @@ KB200_TEAM_FUNCTION void single(const Impl::ThreadSingleStruct& s, const L& f, T
 // ------------------------------------------------------------------------------------------ TeamPolicy launch
 namespace Impl {
 
-constexpr size_t kTeamCollectiveBytes = (1024 + 2) * 16;  // team_scan of <=1024 threads of <=16-byte values
+// Shared memory in front of level-0 scratch for the team collectives: team_scan keeps team_size + 2 values of <= 16 bytes,
+// block-wide reductions 34 values of the reduction type.  Sized per launch: a fixed worst case (16 KiB) would shrink the L1 data
+// cache of every small-team kernel (13 CTAs x 16 KiB of carve-out left 43 KB of L1 for the SpMV gather: 2.8x slower than with it).
+constexpr size_t kTeamCollectiveMin = 4096;  // nested team reductions of value types up to 120 bytes whatever the top-level type
+KB200_FUNCTION constexpr size_t team_collective_bytes(int team_size, size_t value_bytes) {
+  size_t c = kTeamCollectiveMin;
+  if ((size_t)(team_size + 2) * 16 > c) c = (size_t)(team_size + 2) * 16;
+  if (value_bytes * 34 > c) c = value_bytes * 34;
+  return (c + 15) & ~(size_t)15;
+}
 
 struct TeamLaunchParams {
   int league_size;
+  size_t coll_bytes;    // collective area in front of level-0 scratch (team_collective_bytes)
   size_t l0_team, l0_thread, l1_team, l1_thread;
   char* l1_arena;       // grid * l1_per_team bytes
   size_t l1_per_team;
@@ -514,10 +538,11 @@ template <class F, class Tag>
 __global__ void team_for_kernel(const __grid_constant__ F f, const TeamLaunchParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   for (int lr = blockIdx.x; lr < p.league_size; lr += gridDim.x) {
-    B200TeamMember m(smem, smem + kTeamCollectiveBytes, p.l0_team, p.l0_thread, p.l1_arena + (size_t)blockIdx.x * p.l1_per_team,
+    B200TeamMember m(smem, smem + p.coll_bytes, p.l0_team, p.l0_thread, p.l1_arena + (size_t)blockIdx.x * p.l1_per_team,
                      p.l1_team, p.l1_thread, lr, p.league_size);
     if constexpr (std::is_void<Tag>::value) f(m); else f(Tag{}, m);
-    if (lr + (int)gridDim.x < p.league_size) __syncthreads();  // scratch is reused by the next league member
+    // user scratch is reused by the next league member (the collective area is fenced by the collectives themselves)
+    if (p.l0_team + p.l0_thread + p.l1_team + p.l1_thread != 0 && lr + (int)gridDim.x < p.league_size) __syncthreads();
   }
 }
 
@@ -530,7 +555,7 @@ __global__ void team_reduce_kernel(const __grid_constant__ F f, const __grid_con
   V acc;
   red.init(acc);
   for (int lr = blockIdx.x; lr < p.league_size; lr += gridDim.x) {
-    B200TeamMember m(smem, smem + kTeamCollectiveBytes, p.l0_team, p.l0_thread, p.l1_arena + (size_t)blockIdx.x * p.l1_per_team,
+    B200TeamMember m(smem, smem + p.coll_bytes, p.l0_team, p.l0_thread, p.l1_arena + (size_t)blockIdx.x * p.l1_per_team,
                      p.l1_team, p.l1_thread, lr, p.league_size);
     if constexpr (std::is_void<Tag>::value) f(m, acc); else f(Tag{}, m, acc);
     if (lr + (int)gridDim.x < p.league_size) __syncthreads();
@@ -570,9 +595,8 @@ struct TeamShape {
     p.l0_team = pol.team_scratch_size(0) + functor_shmem(f, team); p.l0_thread = pol.thread_scratch_size(0);
     p.l1_team = pol.team_scratch_size(1); p.l1_thread = pol.thread_scratch_size(1);
     const size_t l0 = p.l0_team + p.l0_thread * team;
-    size_t coll = kTeamCollectiveBytes;
-    if (value_bytes * 34 > coll) coll = value_bytes * 34;
-    smem = coll + l0 + 16;
+    p.coll_bytes = team_collective_bytes(team, value_bytes);
+    smem = p.coll_bytes + l0 + 16;
     if (smem > (size_t)220 * 1024)
       throw std::runtime_error("kb200::TeamPolicy: requested too much level-0 scratch (shared memory) for this team size");
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -622,8 +646,7 @@ int team_size_from_attr(const Policy& pol, const F& f, const cudaFuncAttributes&
   int team = max_threads / vec;
   // level-0 scratch (policy request + what the functor asks for itself) must fit next to the collective area
   while (team > 1) {
-    size_t coll = kTeamCollectiveBytes;
-    if (value_bytes * 34 > coll) coll = value_bytes * 34;
+    const size_t coll = team_collective_bytes(team, value_bytes);
     const size_t l0 = pol.team_scratch_size(0) + TeamShape<Policy>::functor_shmem(f, team) + pol.thread_scratch_size(0) * (size_t)team;
     if (coll + l0 + 16 <= (size_t)220 * 1024) break;
     team /= 2;
@@ -690,7 +713,7 @@ __global__ void array_team_reduce_kernel(const __grid_constant__ F f, const Team
   T acc[CAP];
   ArrayOps<F, T>::init(f, acc, count);
   for (int lr = blockIdx.x; lr < p.league_size; lr += gridDim.x) {
-    B200TeamMember m(smem, smem + kTeamCollectiveBytes, p.l0_team, p.l0_thread, p.l1_arena + (size_t)blockIdx.x * p.l1_per_team,
+    B200TeamMember m(smem, smem + p.coll_bytes, p.l0_team, p.l0_thread, p.l1_arena + (size_t)blockIdx.x * p.l1_per_team,
                      p.l1_team, p.l1_thread, lr, p.league_size);
     if constexpr (std::is_void<Tag>::value) f(m, acc); else f(Tag{}, m, acc);
     if (lr + (int)gridDim.x < p.league_size) __syncthreads();

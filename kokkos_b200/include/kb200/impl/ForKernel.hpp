@@ -52,8 +52,11 @@ struct RangeForLaunch {
     }
     return cached;
   }
-  // waves <= 0: one block per tile (plain grid); waves > 0: persistent grid of SMs*resident*waves/… blocks
-  static int run(b200_instance* inst, const Body& body, int64 n_units, int blocks_per_sm_cap = 0) {
+  // blocks_per_sm_cap <= 0: one block per tile (plain grid); > 0: persistent grid of SMs x min(resident, cap) x waves blocks.
+  // waves > 1 oversubscribes the machine a little: each block still walks many tiles, but the hardware block scheduler evens out
+  // what a fixed tile->block assignment cannot when iterations differ in latency (random atomics: the last blocks of a one-wave grid
+  // finish 9% late -- profiles/r02_for_waves.log).
+  static int run(b200_instance* inst, const Body& body, int64 n_units, int blocks_per_sm_cap = 0, int waves = 1) {
     static_assert(sizeof(Body) <= 32000, "closure exceeds the kernel parameter space");
     HostRuntime rt(inst);
     constexpr int64 TILE = (int64)BLOCK * UNROLL;
@@ -66,7 +69,7 @@ struct RangeForLaunch {
     if (blocks_per_sm_cap > 0) {
       int bps = resident_blocks_per_sm();
       if (blocks_per_sm_cap < bps) bps = blocks_per_sm_cap;
-      const int64 cap = (int64)rt.sm_count() * bps;
+      const int64 cap = (int64)rt.sm_count() * bps * (waves > 1 ? waves : 1);
       if (grid > cap) grid = cap;
     }
     if (grid > 0x7fffffffll) grid = 0x7fffffffll;

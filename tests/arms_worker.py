@@ -42,6 +42,9 @@ def main():
             assert np.array_equal(y.cpu().numpy(), exp_y), (A.ARM_NAMES[arm], n, "scan")
             if arm != A.CUB:
                 assert tot.item() == exp_tot, (A.ARM_NAMES[arm], n, "scan total")
+            y.fill_(-7)
+            arms.std_exclusive_scan(arm, dxi.data_ptr(), y.data_ptr(), n)   # Kokkos::Experimental::exclusive_scan (typed route on B200)
+            assert np.array_equal(y.cpu().numpy(), exp_y), (A.ARM_NAMES[arm], n, "std exclusive_scan")
         # stream copy / triad
         b, c = t(W.c1_general(n)), t(W.c1_uniform(n))
         for arm in (A.B200, A.CUDA):

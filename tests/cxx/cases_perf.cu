@@ -167,20 +167,19 @@ int kb200_perf_scan_variant(int variant, i64 n, int warm, int reps, double* out_
     };
     switch (variant) {
       case 0: run(Impl::GenericScan<Pol, F, Red>{}); break;
-      case 1: run(Impl::GenericScan<Pol, F, Red, 256, 13>{}); break;
-      case 2: run(Impl::GenericScan<Pol, F, Red, 256, 17>{}); break;
-      case 3: run(Impl::GenericScan<Pol, F, Red, 512, 9>{}); break;
-      case 4: run(Impl::GenericScan<Pol, F, Red, 512, 13>{}); break;
-      case 5: run(Impl::GenericScan<Pol, F, Red, 128, 17>{}); break;
-      case 6: run(Impl::GenericScan<Pol, F, Red, 128, 9>{}); break;
-      case 7: run(Impl::GenericScan<Pol, F, Red, 1024, 9>{}); break;
-      case 8: run(Impl::GenericScan<Pol, F, Red, 256, 21>{}); break;
-      case 9: run(Impl::GenericScan<Pol, F, Red, 256, 25>{}); break;
-      case 10: run(Impl::GenericScan<Pol, F, Red, 512, 17>{}); break;
-      case 11: run(Impl::GenericScan<Pol, F, Red, 512, 21>{}); break;
-      case 12: run(Impl::GenericScan<Pol, F, Red, 1024, 13>{}); break;
-      case 13: run(Impl::GenericScan<Pol, F, Red, 1024, 17>{}); break;
-      case 14: run(Impl::GenericScan<Pol, F, Red, 128, 25>{}); break;
+      case 1: run(Impl::GenericScan<Pol, F, Red, 1024, 17, 1>{}); break;
+      case 2: run(Impl::GenericScan<Pol, F, Red, 1024, 13, 4>{}); break;
+      case 3: run(Impl::GenericScan<Pol, F, Red, 512, 13, 4>{}); break;
+      case 4: run(Impl::GenericScan<Pol, F, Red, 512, 17, 4>{}); break;
+      case 5: run(Impl::GenericScan<Pol, F, Red, 512, 13, 8>{}); break;
+      case 6: run(Impl::GenericScan<Pol, F, Red, 1024, 19, 2>{}); break;
+      case 7: run(Impl::GenericScan<Pol, F, Red, 1024, 21, 2>{}); break;
+      case 8: run(Impl::GenericScan<Pol, F, Red, 256, 13, 8>{}); break;
+      case 9: run(Impl::GenericScan<Pol, F, Red, 512, 21, 4>{}); break;
+      case 10: run(Impl::GenericScan<Pol, F, Red, 768, 13, 4>{}); break;
+      case 11: run(Impl::GenericScan<Pol, F, Red, 1024, 13, 8>{}); break;
+      case 12: run(Impl::GenericScan<Pol, F, Red, 512, 25, 4>{}); break;
+      case 13: run(Impl::GenericScan<Pol, F, Red, 1024, 21, 4>{}); break;
       default: return -1;
     }
     *total = t;

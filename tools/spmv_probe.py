@@ -32,7 +32,7 @@ y = torch.empty(R, dtype=torch.float64, device=dev)
 nbytes = nnz * 12 + R * 16 + 8 * R
 V = lambda t, dt: space.wrap(t.data_ptr(), t.numel(), dt)  # noqa: E731
 ref = None
-for vl, ur in ((32, 1), (32, 2), (32, 4), (32, 8), (16, 1), (16, 2), (16, 4), (16, 8), (8, 4), (8, 8)):
+for vl, ur in ((32, 1), (16, 1), (8, 1), (8, 2), (4, 1), (4, 2)):
     kb.tune_set("spmv.vl", vl); kb.tune_set("spmv.ur", ur)
     fn = lambda: space.spmv_crs(V(row_map, np.int64), V(col, np.int32), V(val, np.float64), V(x, np.float64), V(y, np.float64))  # noqa: E731
     fn(); torch.cuda.synchronize()
