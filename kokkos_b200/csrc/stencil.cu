@@ -63,23 +63,25 @@ KB200_DEVICE_FUNCTION void stencil_update(V& acc, double v, int i, int j, int k,
   if (v > acc.max_val || (v == acc.max_val && loc < acc.max_loc)) { acc.max_val = v; acc.max_loc = loc; }
 }
 
+// jstep/kstep > 1: only every jstep-th row of every kstep-th plane is visited (the sampling pre-pass of the TMA path)
 template <int BLOCK, int UNROLL>
 __global__ void __launch_bounds__(BLOCK) stencil7_minmaxloc_kernel(const double* __restrict__ u, double* __restrict__ vout,
                                                                     int64 n0, int64 n1, int64 n2, double c0, double c1,
-                                                                    ReduceScratch scratch) {
+                                                                    ReduceScratch scratch, int jstep = 1, int kstep = 1) {
   __shared__ __align__(16) unsigned char smem[32 * sizeof(V)];
   const StencilRed red;
   V acc;
   red.init(acc);
   const int lane = threadIdx.x & 31;
   const int64 warps_per_grid = (int64)gridDim.x * (BLOCK / 32);
-  const int64 m1 = n1 - 2, m2 = n2 - 2;
+  const int64 m1 = (n1 - 2 + jstep - 1) / jstep, m2 = (n2 - 2 + kstep - 1) / kstep;
   const int64 rows = m1 * m2;
   const int64 sj = n0, sk = n0 * n1;
   // consecutive warps of a block take consecutive rows (j fastest) so j+-1 neighbours share L1
   for (int64 row = (int64)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); row < rows; row += warps_per_grid) {
-    const int64 k = row / m1 + 1;
-    const int64 j = row - (k - 1) * m1 + 1;
+    const int64 kq = row / m1;
+    const int64 k = kq * kstep + 1;
+    const int64 j = (row - kq * m1) * jstep + 1;
     const double* c = u + j * sj + k * sk;
     for (int64 i0 = 1; i0 < n0 - 1; i0 += 32 * UNROLL) {
       double ctr[UNROLL], xm[UNROLL], xp[UNROLL], ym[UNROLL], yp[UNROLL], zm[UNROLL], zp[UNROLL];
@@ -229,6 +231,7 @@ struct StencilTmaParams {
   int n0, n1, n2;
   int kc, tiles_j, tiles_k;
   double c0, c1;
+  const V* seed;  // MinMaxLoc over a sparse sample of the same points (or nullptr): every thread starts from it
   int dbg;  // tools/stencil_probe.py experiments only: 1 = consumers skip the arithmetic (pure data movement), 2 = no data movement (pure arithmetic on stale smem)
 };
 
@@ -301,6 +304,10 @@ __global__ void __launch_bounds__(CT + (PW ? 32 : 0), 1) stencil7_tma_kernel(con
   const StencilRed red;
   V acc;
   red.init(acc);
+  // Candidate thresholds from a sparse sample of the SAME values (true candidates with their locations, so the exact result is
+  // unchanged): without them a smooth field, whose running extrema move with every plane, takes the re-evaluation path in
+  // nearly every step (0.41 ms instead of 0.23 ms at 512^3).
+  if (p.seed) acc = *p.seed;
   const int ntiles = p.tiles_j * p.tiles_k;
 
   StencilProducer<BJ, NS> prod;
@@ -456,13 +463,28 @@ int launch_tma(b200_instance* I, const double* u, double* v_out, int n0, int n1,
   const int tiles_k = (n2 - 2 + kc - 1) / kc;
   const long ntiles = (long)tiles_j * tiles_k;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
+  // sampling pre-pass: every 16th row of every 16th plane (5 rows read per sampled row: ~2 % of the field)
+  constexpr int SBLOCK = 256, SUNROLL = 4, SSTEP = 16;
+  const long srows = (long)((n1 - 2 + SSTEP - 1) / SSTEP) * ((n2 - 2 + SSTEP - 1) / SSTEP);
+  const bool sample = b200_tune("stencil.seed", 1) && (long)(n1 - 2) * (n2 - 2) >= 16384;
+  long sgrid = (srows + SBLOCK / 32 - 1) / (SBLOCK / 32);
+  if (sgrid > 4L * sms) sgrid = 4L * sms;
+  const size_t nparts = (size_t)(sample && sgrid > grid ? sgrid : grid);
   ReduceScratch s;
   void *slot_dev = nullptr, *slot_host = nullptr;
   int rc;
-  if ((rc = rt.reduce_scratch((size_t)grid * sizeof(V), sizeof(V), rh != nullptr, &s.partials, &s.ticket, &slot_dev, &slot_host))) return rc;
+  if ((rc = rt.reduce_scratch((nparts + 1) * sizeof(V), sizeof(V), rh != nullptr, &s.partials, &s.ticket, &slot_dev, &slot_host))) return rc;
+  V* const seed = reinterpret_cast<V*>(s.partials) + nparts;  // one slot behind the per-block partials
+  if (sample) {
+    ReduceScratch ss = s;
+    ss.result0 = seed;
+    ss.result1 = nullptr;
+    stencil7_minmaxloc_kernel<SBLOCK, SUNROLL><<<(unsigned)sgrid, SBLOCK, 0, rt.stream()>>>(u, nullptr, n0, n1, n2, c0, c1, ss, SSTEP, SSTEP);
+    if ((rc = rt.check_launch("b200_stencil7_minmaxloc_f64 (sample)"))) return rc;
+  }
   s.result0 = rh ? slot_dev : (void*)rd;
   s.result1 = rh ? (void*)rd : nullptr;
-  StencilTmaParams p{u, v_out, n0, n1, n2, kc, tiles_j, tiles_k, c0, c1, b200_tune("stencil.dbg", 0)};
+  StencilTmaParams p{u, v_out, n0, n1, n2, kc, tiles_j, tiles_k, c0, c1, sample ? seed : nullptr, b200_tune("stencil.dbg", 0)};
   kern<<<grid, CT + (PW ? 32 : 0), smem, rt.stream()>>>(p, s);
   if ((rc = rt.check_launch(where))) return rc;
   if (rh) {

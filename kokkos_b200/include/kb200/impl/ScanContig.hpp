@@ -187,6 +187,11 @@ KB200_DEVICE_FUNCTION T lookback_sum(const ScanDesc16* desc, int64 tile, unsigne
   }
 }
 
+// Tried and dropped (profiles/r02_scan_assist_probe.log): an "assisted" look-back in which every look-back also publishes the
+// inclusive prefixes of the tiles inside its window (suffix sums over the lanes) and owners first check whether their own
+// descriptor was upgraded.  It shortens the chain but costs up to 31 extra 16-byte stores and one more load per tile:
+// 5.89 TB/s against 6.18 TB/s for the plain look-back above at 2^30 int64.
+
 // NV = 16-byte vectors per thread (odd).  ITEMS = NV*16/sizeof(T).
 template <class T, int BLOCK, int NV, int NBUF, int LBW, bool INCLUSIVE>
 __global__ void __launch_bounds__(BLOCK) contig_scan_kernel(const ScanContigParams<T> p) {

@@ -29,7 +29,9 @@ def test_general_double_sum_at_2_27_within_tolerance_of_exact(space, ref, gen):
     dev_ours, dev_ref = abs(got - exact) / scale, abs(theirs - exact) / scale
     print(f"{gen.__name__} 2^27: ours {got!r} reference {theirs!r} exact {exact!r}; relative deviation ours {dev_ours:.3e} reference {dev_ref:.3e}")
     assert dev_ours <= REL_TOL, (got, exact, dev_ours)
-    assert dev_ref <= REL_TOL, (theirs, exact, dev_ref)
+    # the reference's per-thread left-to-right sums drift further from the exact value than 1e-12 at this size (6.8e-12 with 4 threads
+    # on c1_general); ours must agree with it to within ITS deviation plus the tolerance
+    assert abs(got - theirs) / scale <= dev_ref + REL_TOL, (got, theirs, dev_ref)
 
 
 def test_c4_stencil_512_values_and_locations_equal_the_live_reference(space, ref):
