@@ -626,6 +626,16 @@ class Bench:
                 am[nm] = self.timed(lambda: self.arms.spmv(arm, R, row_map.data_ptr(), col.data_ptr(), val.data_ptr(), xg.data_ptr(), y.data_ptr(), nnz, ncols))
                 assert torch.equal(y, exp_y), f"SpMV mismatch ({nm})"
         entry("C5b_spmv_crs_2^22rows_x32", nbytes, ms, {"sharding": "rows sharded, x replicated: no exchange"}, am)
+        del row_map, col, val, xg, y, exp_y
+
+        # ---- launch latency (benchmarks/launch_latency): Kokkos user calls, host clock, 1000 launches per figure
+        if self.arms and rank == 0:
+            scratch = torch.zeros((1 << 16) + 8, dtype=torch.float64, device=dev)
+            lat = {}
+            for arm, nm in ((A.B200, "Kokkos::B200"), (A.CUDA, "Kokkos::Cuda")):
+                lat[nm] = {f"{opn} n={n}": round(self.arms.launch_latency_us(arm, op, n, 1000, scratch.data_ptr()), 2)
+                           for op, opn in ((0, "parallel_for"), (1, "parallel_reduce->View"), (2, "parallel_reduce->scalar")) for n in (1, 1 << 16)}
+            res["launch_latency_us"] = lat
         return res
 
     # ---- e2e: the same step through the host-buffer C-ABI calls -------------------------------------------------------

@@ -33,6 +33,8 @@ class Arms:
         L.kka_stream_copy_f64.argtypes = [c_int, c_void_p, c_void_p, c_int64]
         L.kka_stream_triad_f64.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_double, c_int64]
         L.kka_stencil7_minmaxloc_f64.argtypes = [c_int, c_void_p, c_int64, c_int64, c_int64, c_double, c_double, c_void_p]
+        L.kka_stencil7_minmaxloc_f64_tiled.argtypes = [c_int, c_void_p, c_int64, c_int64, c_int64, c_double, c_double, c_void_p, c_int64, c_int64, c_int64]
+        L.kka_launch_latency_us.argtypes = [c_int, c_int, c_int64, c_int, c_void_p, ctypes.POINTER(c_double)]
         L.kka_gups_add_i64.argtypes = [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64]
         L.kka_spmv_crs_f64.argtypes = [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64]
         self._ok(L.kka_init(device, stream))
@@ -59,6 +61,14 @@ class Arms:
 
     def stencil7_minmaxloc(self, arm, u_ptr, n0, n1, n2, c0, c1, result_dev_ptr):
         self._ok(self.lib.kka_stencil7_minmaxloc_f64(arm, u_ptr, n0, n1, n2, c0, c1, result_dev_ptr))
+
+    def stencil7_minmaxloc_tiled(self, arm, u_ptr, n0, n1, n2, c0, c1, result_dev_ptr, tile):
+        self._ok(self.lib.kka_stencil7_minmaxloc_f64_tiled(arm, u_ptr, n0, n1, n2, c0, c1, result_dev_ptr, *tile))
+
+    def launch_latency_us(self, arm, op, n, batch, scratch_dev_ptr):
+        out = c_double()
+        self._ok(self.lib.kka_launch_latency_us(arm, op, n, batch, scratch_dev_ptr, ctypes.byref(out)))
+        return out.value
 
     def gups_add(self, arm, table_ptr, table_len, idx_ptr, m, datum):
         self._ok(self.lib.kka_gups_add_i64(arm, table_ptr, table_len, idx_ptr, m, datum))

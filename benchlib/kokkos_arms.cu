@@ -15,6 +15,7 @@
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <chrono>
 #include <cstdint>
 #include <memory>
 #include <string>
@@ -117,15 +118,18 @@ void stream_triad(const Space& s, double* a_, const double* b_, const double* c_
 
 using MML = Kokkos::MinMaxLoc<double, i64, Kokkos::CudaSpace>;
 template <class Space>
-void stencil7_minmaxloc(const Space& s, const double* u_, i64 n0, i64 n1, i64 n2, double c0, double c1, MML::value_type* result_dev) {
+void stencil7_minmaxloc(const Space& s, const double* u_, i64 n0, i64 n1, i64 n2, double c0, double c1, MML::value_type* result_dev,
+                        i64 t0 = 0, i64 t1 = 0, i64 t2 = 0) {
   DField<const double> u(u_, (size_t)n0, (size_t)n1, (size_t)n2);
   Kokkos::View<MML::value_type, Kokkos::CudaSpace, Kokkos::MemoryTraits<Kokkos::Unmanaged>> r(result_dev);
-  using Policy = Kokkos::MDRangePolicy<Space, Kokkos::Rank<3>, Kokkos::IndexType<i64>>;
-  Kokkos::parallel_reduce("arms::stencil7", Policy(s, {1, 1, 1}, {n0 - 1, n1 - 1, n2 - 1}),
-                          KOKKOS_LAMBDA(const i64 i, const i64 j, const i64 k, MML::value_type& m) {
+  using Policy = Kokkos::MDRangePolicy<Space, Kokkos::Rank<3>>;  // default index type, as in the reference's own MDRange tests
+  // t0 == 0: the backend's default tile (what a user who does not tune gets)
+  const Policy policy = t0 > 0 ? Policy(s, {1, 1, 1}, {n0 - 1, n1 - 1, n2 - 1}, {t0, t1, t2}) : Policy(s, {1, 1, 1}, {n0 - 1, n1 - 1, n2 - 1});
+  Kokkos::parallel_reduce("arms::stencil7", policy,
+                          KOKKOS_LAMBDA(const int i, const int j, const int k, MML::value_type& m) {
                             const double nb = nf_add(nf_add(nf_add(nf_add(nf_add(u(i - 1, j, k), u(i + 1, j, k)), u(i, j - 1, k)), u(i, j + 1, k)), u(i, j, k - 1)), u(i, j, k + 1));
                             const double v = nf_add(nf_mul(c0, u(i, j, k)), nf_mul(c1, nb));
-                            const i64 loc = (i * n1 + j) * n2 + k;
+                            const i64 loc = ((i64)i * n1 + j) * n2 + k;
                             if (v < m.min_val || (v == m.min_val && loc < m.min_loc)) { m.min_val = v; m.min_loc = loc; }
                             if (v > m.max_val || (v == m.max_val && loc < m.max_loc)) { m.max_val = v; m.max_loc = loc; }
                           }, MML(r));
@@ -162,6 +166,28 @@ void spmv(const Space& s, i64 nrows, const i64* row_map_, const int* col_, const
       Kokkos::single(Kokkos::PerThread(t), [&]() { y(row) = acc; });
     });
   });
+}
+
+// benchmarks/launch_latency/launch_latency.cpp in miniature: `batch` back-to-back launches over n elements, host clock around the
+// batch including the closing fence.  op 0: parallel_for; 1: parallel_reduce into a device View (asynchronous); 2: parallel_reduce
+// into a host scalar (each call fences).
+template <class Space>
+double launch_latency_us(const Space& s, int op, i64 n, int batch, double* scratch_dev) {
+  DView<double> a(scratch_dev, (size_t)(n > 0 ? n : 1));
+  DScalar<double> r(scratch_dev + (n > 0 ? n : 1));
+  using Policy = Kokkos::RangePolicy<Space, Kokkos::IndexType<i64>>;
+  auto one = [&]() {
+    if (op == 0) Kokkos::parallel_for("arms::lat_for", Policy(s, 0, n), KOKKOS_LAMBDA(const i64 i) { a(i) = 1.0; });
+    else if (op == 1) Kokkos::parallel_reduce("arms::lat_red_view", Policy(s, 0, n), KOKKOS_LAMBDA(const i64 i, double& u) { u += a(i); }, r);
+    else { double h = 0; Kokkos::parallel_reduce("arms::lat_red_scalar", Policy(s, 0, n), KOKKOS_LAMBDA(const i64 i, double& u) { u += a(i); }, h); }
+  };
+  for (int k = 0; k < 20; ++k) one();
+  s.fence();
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int k = 0; k < batch; ++k) one();
+  s.fence();
+  const auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double, std::micro>(t1 - t0).count() / batch;
 }
 
 template <class F>
@@ -235,6 +261,13 @@ int kka_stream_triad_f64(int arm, double* a, const double* b, const double* c, d
 int kka_stencil7_minmaxloc_f64(int arm, const double* u, i64 n0, i64 n1, i64 n2, double c0, double c1, void* result_dev) {
   static_assert(sizeof(MML::value_type) == 32, "MinMaxLoc value layout");
   return dispatch(arm, [&](auto& s) { stencil7_minmaxloc(s, u, n0, n1, n2, c0, c1, (MML::value_type*)result_dev); });
+}
+int kka_stencil7_minmaxloc_f64_tiled(int arm, const double* u, i64 n0, i64 n1, i64 n2, double c0, double c1, void* result_dev, i64 t0, i64 t1, i64 t2) {
+  return dispatch(arm, [&](auto& s) { stencil7_minmaxloc(s, u, n0, n1, n2, c0, c1, (MML::value_type*)result_dev, t0, t1, t2); });
+}
+// scratch_dev: at least n + 1 doubles of device memory
+int kka_launch_latency_us(int arm, int op, i64 n, int batch, double* scratch_dev, double* out_us) {
+  return dispatch(arm, [&](auto& s) { *out_us = launch_latency_us(s, op, n, batch, scratch_dev); });
 }
 int kka_gups_add_i64(int arm, i64* table, i64 table_len, const i64* idx, i64 m, i64 datum) {
   return dispatch(arm, [&](auto& s) { gups_add(s, table, table_len, idx, m, datum); });
