@@ -202,7 +202,8 @@ void array_reduce(const KbPolicy& policy, const Functor& f, int count, T* host, 
   int rc;
   if (count <= 8) rc = kb200::Impl::array_reduce_launch<T, Tag>(policy, f, count, host, dev, std::integral_constant<int, 8>{});
   else if (count <= 32) rc = kb200::Impl::array_reduce_launch<T, Tag>(policy, f, count, host, dev, std::integral_constant<int, 32>{});
-  else rc = kb200::Impl::array_reduce_launch<T, Tag>(policy, f, count, host, dev, std::integral_constant<int, 64>{});
+  else if (count <= 64) rc = kb200::Impl::array_reduce_launch<T, Tag>(policy, f, count, host, dev, std::integral_constant<int, 64>{});
+  else rc = kb200::Impl::array_reduce_launch_big<T, Tag>(policy, f, count, host, dev);  // any length: accumulators in global memory
   kb200::Impl::throw_on_error(rc);
 }
 }  // namespace B200Adapter

@@ -271,6 +271,40 @@ int array_reduce_launch(const MDRangePolicy<P...>& policy_in, const F& f, int co
 template <class T, class Tag, class F, class... P, int CAP>
 int array_reduce_launch(const TeamPolicy<P...>& pol, const F& f, int count, T* rh, T* rd, std::integral_constant<int, CAP>);  // Team.hpp
 
+// value_count > 64: accumulator arrays in global memory (ArrayReduceKernel.hpp, "big" kernels)
+template <class T, class Tag, class F, class... P>
+int array_reduce_launch_big(const RangePolicy<P...>& policy, const F& f, int count, T* rh, T* rd) {
+  using Index = typename RangePolicy<P...>::index_type;
+  constexpr int BLOCK = 128;
+  b200_instance* inst = policy.space().impl_instance();
+  HostRuntime rt(inst);
+  const int64 n = (int64)(policy.end() - policy.begin()) > 0 ? (int64)(policy.end() - policy.begin()) : 0;
+  const int64 blocks = (n + BLOCK - 1) / BLOCK, cap = (int64)rt.sm_count() * 2;
+  const int grid = array_big_grid(blocks < cap ? blocks : cap, BLOCK, count, sizeof(T));
+  return array_reduce_big_run<T>(inst, count, grid, BLOCK, rh, rd, [&](T* slabs, unsigned* ticket, T* dst) {
+    array_range_reduce_big_kernel<F, Tag, Index, T><<<grid, BLOCK, 0, rt.stream()>>>(f, policy.begin(), n, count, slabs, ticket, dst);
+  });
+}
+template <class T, class Tag, class F, class... P>
+int array_reduce_launch_big(const MDRangePolicy<P...>& policy, const F& f, int count, T* rh, T* rd) {
+  using Policy = MDRangePolicy<P...>;
+  using Index = typename Policy::index_type;
+  b200_instance* inst = policy.space().impl_instance();
+  HostRuntime rt(inst);
+  MDLaunchShape<Policy> sh(policy);
+  const long long cap = (long long)rt.sm_count() * 2, tiles = sh.p.num_tiles;
+  const int grid = array_big_grid(tiles < cap ? tiles : cap, sh.threads, count, sizeof(T));
+  sh.set_grid(grid);
+  if (tiles < 1) { sh.p.num_tiles = 0; sh.block = dim3(32, 1, 1); sh.threads = 32; }
+  return array_reduce_big_run<T>(inst, count, grid, sh.threads, rh, rd, [&](T* slabs, unsigned* ticket, T* dst) {
+    array_mdrange_reduce_big_kernel<F, Tag, T, Policy::rank, Index><<<grid, sh.block, 0, rt.stream()>>>(f, sh.p, count, slabs, ticket, dst);
+  });
+}
+template <class T, class Tag, class F, class... P>
+int array_reduce_launch_big(const TeamPolicy<P...>&, const F&, int, T*, T*) {
+  return b200_report_error(B200_EUNSUPPORTED, "kb200::parallel_reduce(TeamPolicy, value_type[]): value_count above 64 is not supported");
+}
+
 template <class Policy, class F, class R>
 void array_reduce_entry(const Policy& policy, const F& f, R&& result) {
   using T = std::remove_extent_t<typename F::value_type>;
@@ -287,7 +321,8 @@ void array_reduce_entry(const Policy& policy, const F& f, R&& result) {
   int rc;
   if (count <= 8) rc = array_reduce_launch<T, Tag>(policy, f, count, rh, rd, std::integral_constant<int, 8>{});
   else if (count <= 32) rc = array_reduce_launch<T, Tag>(policy, f, count, rh, rd, std::integral_constant<int, 32>{});
-  else rc = array_reduce_launch<T, Tag>(policy, f, count, rh, rd, std::integral_constant<int, 64>{});
+  else if (count <= 64) rc = array_reduce_launch<T, Tag>(policy, f, count, rh, rd, std::integral_constant<int, 64>{});
+  else rc = array_reduce_launch_big<T, Tag>(policy, f, count, rh, rd);
   throw_on_error(rc);
 }
 

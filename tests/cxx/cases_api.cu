@@ -803,3 +803,32 @@ int kb200_case_mdrange_heavy(i64 n0, i64 n1, i64 n2, unsigned long long* hy) {
 }
 
 }  // extern "C"
+
+// ---- runtime-length array reductions of ANY length (value_type = T[], value_count; FunctorAnalysis.hpp:865-958): above 64 elements
+// the accumulators live in global memory (impl/ArrayReduceKernel.hpp, "big" kernels)
+namespace {
+struct BigHistogram {
+  using value_type = i64[];
+  unsigned value_count;
+  KB200_INLINE_FUNCTION void operator()(const i64 i, i64 dst[]) const { dst[i % (i64)value_count] += i; }
+};
+struct BigHistogramMD {
+  using value_type = i64[];
+  unsigned value_count;
+  KB200_INLINE_FUNCTION void operator()(const int i, const int j, i64 dst[]) const { dst[(i * 7 + j) % (int)value_count] += 1 + j; }
+  KB200_INLINE_FUNCTION void init(i64 dst[]) const { for (unsigned c = 0; c < value_count; ++c) dst[c] = 0; }
+  KB200_INLINE_FUNCTION void join(i64 dst[], const i64 src[]) const { for (unsigned c = 0; c < value_count; ++c) dst[c] += src[c]; }
+  KB200_INLINE_FUNCTION void final(i64 dst[]) const { dst[0] += 1000000; }
+};
+}  // namespace
+extern "C" int kb200_case_array_reduce_big(i64 n, int count, i64 n0, i64 n1, i64* out_range, i64* out_md) {
+  return guarded([&] {
+    parallel_reduce("big array", RangePolicy<>(0, n), BigHistogram{(unsigned)count}, out_range);                    // result: host array
+    View<i64*> r("r", (size_t)count);
+    parallel_reduce("big array md", MDRangePolicy<Rank<2>>({0, 0}, {n0, n1}), BigHistogramMD{(unsigned)count}, r);  // result: device View
+    fence();
+    auto h = create_mirror_view_and_copy(HostSpace(), r);
+    for (int c = 0; c < count; ++c) out_md[c] = h(c);
+    return 0;
+  });
+}

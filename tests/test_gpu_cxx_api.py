@@ -296,3 +296,22 @@ def test_unique_token_and_resize(cases):
     assert out[5] == h and out[6] == h * (h + 1) // 2
     assert out[7] == 84 and out[8] == sum(10 * i + j for i in range(5) for j in range(4)) and out[9] == 0
 
+
+
+@pytest.mark.parametrize("count", [65, 300, 4097])
+def test_runtime_length_array_reduce_of_any_length(cases, count):
+    """value_type[] reductions above the 64-element register capacity: accumulators in global memory; Range with
+    the default init/join (+=), MDRange with the functor's own init/join/final."""
+    n, n0, n1 = 200003, 97, 53
+    out_r = np.zeros(count, dtype=np.int64)
+    out_m = np.zeros(count, dtype=np.int64)
+    ok(cases, cases.kb200_case_array_reduce_big(c_int64(n), c_int(count), c_int64(n0), c_int64(n1), P(out_r), P(out_m)))
+    i = np.arange(n, dtype=np.int64)
+    exp_r = np.bincount(i % count, weights=None, minlength=count) * 0
+    np.add.at(exp_r, i % count, i)
+    assert np.array_equal(out_r, exp_r)
+    ii, jj = np.meshgrid(np.arange(n0), np.arange(n1), indexing="ij")
+    exp_m = np.zeros(count, dtype=np.int64)
+    np.add.at(exp_m, ((ii * 7 + jj) % count).ravel(), (1 + jj).ravel())
+    exp_m[0] += 1000000
+    assert np.array_equal(out_m, exp_m)
