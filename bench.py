@@ -320,22 +320,22 @@ class Bench:
         sp = self.sp
         scan_ev = []
 
-        overlap = self.args.overlap
-        if overlap:
-            # two execution-space instances (as a Kokkos program would use two Kokkos::Cuda instances): the reduce and its
-            # all-reduce run on stream B while the scan runs on the main stream; every step forks and joins with events
-            self.streamB = torch.cuda.Stream(device=self.dev)
-            with torch.cuda.stream(self.streamB):
-                self.spaceB = self.kb.B200(self.local_rank, stream=self.streamB.cuda_stream)
-                from kokkos_b200.sharded import ShardedB200
-                spB = ShardedB200(self.spaceB, coll_device=self.dev)
-                vxdB = self.spaceB.wrap(self.xd.data_ptr(), self.n, self.np.float64)
-            ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+        # two execution-space instances (as a Kokkos program would use two Kokkos::Cuda instances): the reduce and its all-reduce
+        # can run on stream B while the scan runs on the main stream; every step then forks and joins with events.  Whether that
+        # pays depends on N: on one GPU each kernel saturates HBM by itself, with the distributed scan (latency bound) it does.
+        self.streamB = torch.cuda.Stream(device=self.dev)
+        with torch.cuda.stream(self.streamB):
+            self.spaceB = self.kb.B200(self.local_rank, stream=self.streamB.cuda_stream)
+            from kokkos_b200.sharded import ShardedB200
+            spB = ShardedB200(self.spaceB, coll_device=self.dev)
+            vxdB = self.spaceB.wrap(self.xd.data_ptr(), self.n, self.np.float64)
+        ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+        mode = {"overlap": self.args.overlap}
 
         def step(record=False):
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            if overlap:
+            if mode["overlap"]:
                 ev_fork.record(self.side)
                 self.streamB.wait_event(ev_fork)
                 if record:
@@ -359,6 +359,14 @@ class Bench:
             if record:
                 scan_ev.append((e0, e1))
 
+        if mode["overlap"] < 0:  # auto: 3 untimed-for-the-record steps of each structure, the faster one (max over ranks) is used
+            cand = {}
+            for ov in (0, 1):
+                mode["overlap"] = ov
+                cand[ov] = self.timed(step, steps=3, warmup=2)
+            mode["overlap"] = 1 if cand[1] < cand[0] else 0
+            self.overlap_probe_ms = {"sequential": cand[0], "concurrent": cand[1]}
+        self.overlap = mode["overlap"]
         for _ in range(self.warmup):
             step()
         self.sync_all()
@@ -385,7 +393,7 @@ class Bench:
         self.ms_per_step = self.max_over_ranks(t0.elapsed_time(t1)) / self.steps
         self.scan_ms_in_step = self.max_over_ranks(sum(a.elapsed_time(b) for a, b in scan_ev) / len(scan_ev))
         self.scan_ms = self.scan_ms_in_step
-        if overlap:
+        if self.overlap:
             # the dominant kernel timed ALONE (inside a step it shares the machine with the reduce): same launches, same data
             self.scan_ms = self.timed(lambda: sp.cyclic_scan_async(self.vxi, self.vyi, self.n_global, self.tot_dev), warmup=1)
             self.reduce_ms_alone = self.timed(lambda: sp.reduce_sum_async(self.vxd, out=self.red_dev), warmup=1)
@@ -405,7 +413,7 @@ class Bench:
                 "traffic": traffic if not self.distributed else None, "peak_source": self.peak_src,
                 "algorithmic_bytes_per_launch": 16.0 * self.n_local, "avg_launch_ms": self.scan_ms, "frac_of_8TBs_nominal": achieved / 8000.0,
                 "timing": ("kernel timed alone, %d launches with CUDA events right after the timed steps (inside a step it runs concurrently with the "
-                           "reduce kernel: %.3f ms there)" % (self.steps, self.scan_ms_in_step)) if self.args.overlap else "CUDA events around each launch inside the timed steps"}
+                           "reduce kernel: %.3f ms there)" % (self.steps, self.scan_ms_in_step)) if self.overlap else "CUDA events around each launch inside the timed steps"}
 
     # ---- Kokkos user code on Kokkos::B200 (adapter) and the comparators --------------------------------------------
     def kokkos_api_and_comparators(self):
@@ -689,7 +697,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=LOG2N_DEFAULT, help="elements per GPU and per View = 2^log2n")
-    ap.add_argument("--overlap", type=int, default=1, help="1: reduce and scan of a step run concurrently on two execution-space instances; 0: back to back")
+    ap.add_argument("--overlap", type=int, default=-1, help="1: reduce and scan of a step run concurrently on two execution-space instances; 0: back to back; "
+                                                            "-1 (default): both are timed for 3 steps after the warm-up and the faster one is used")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the C2/C4/C5 legs")
@@ -731,7 +740,8 @@ def main():
                 "config": {"workload": workload_text(args.log2n), "policy": "RangePolicy", "elements_per_gpu_per_view": n,
                            "scan_elements_on_rank0": B.n_local, "algorithmic_bytes_per_step_per_gpu": 24 * n, "parallelism": par,
                            "step": ("the reduce and the scan of a step are issued on two execution-space instances (two streams) and run concurrently; "
-                                    "a step ends when both are done" if args.overlap else "reduce then scan, one stream"),
+                                    "a step ends when both are done" if B.overlap else "reduce then scan, one stream") +
+                                   (" (chosen by timing 3 steps of each structure after the warm-up)" if args.overlap < 0 else ""),
                            "api": "typed C-ABI entry points (b200_reduce_sum_f64, b200_scan_excl_i64 / b200_comm_scan_excl_i64): the same calls at every N; "
                                   "the Kokkos-lambda form of the same step is `kokkos_api`",
                            "l2": "inputs (8 GiB per View) are far larger than the 126 MB L2; no flush needed",
@@ -741,10 +751,11 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": B.launches_per_step * args.steps,
                 "clocks": B.clocks, "kokkos_api": api, "comparators": comp,
                 "breakdown": {"scan_GBs_per_gpu": roofline["achieved"], "scan_ms": B.scan_ms, "scan_ms_inside_step": B.scan_ms_in_step,
-                              "reduce_plus_collectives_ms": (B.reduce_ms_alone if args.overlap else B.ms_per_step - B.scan_ms),
-                              "reduce_GBs_per_gpu": 8.0 * n / ((B.reduce_ms_alone if args.overlap else B.ms_per_step - B.scan_ms) * 1e-3) / 1e9,
-                              "step_structure": ("reduce (+ NCCL all-reduce) on instance B || scan on instance A, fork/join by events every step" if args.overlap
+                              "reduce_plus_collectives_ms": (B.reduce_ms_alone if B.overlap else B.ms_per_step - B.scan_ms),
+                              "reduce_GBs_per_gpu": 8.0 * n / ((B.reduce_ms_alone if B.overlap else B.ms_per_step - B.scan_ms) * 1e-3) / 1e9,
+                              "step_structure": ("reduce (+ NCCL all-reduce) on instance B || scan on instance A, fork/join by events every step" if B.overlap
                                                  else "reduce then scan on one instance"),
+                              "step_structure_probe_ms": getattr(B, "overlap_probe_ms", None),
                               "configs": cfgs}}
         if getattr(B, "arms_error", None):
             line["arms_error"] = B.arms_error

@@ -288,7 +288,7 @@ int comm_scan(b200_comm* C, const char* where, const T* x, T* y, int64_t n_globa
     default: break;
   }
 #endif
-  return LR::run_rounds(C->inst, peers, round_tpr(), nsteps, x, y, n_local, total_host, total_dev);
+  return LR::run_rounds(C->inst, peers, round_tpr(), nsteps, x, y, n_local, total_host, total_dev, b200_tune("scan.pfd", -1));
 }
 
 }  // namespace

@@ -18,6 +18,7 @@ int scan_entry(b200_instance* I, const char* where, const T* x, T* y, int64_t n,
   if (n > 0 && (!x || !y)) return b200_set_error(B200_EINVAL, where, "x or y is NULL");
   const int nv = b200_tune("scan.nv", 9), nbuf = b200_tune("scan.nbuf", 4), lbw = b200_tune("scan.lbw", 1);
   const int block = b200_tune("scan.block", 128), bps = b200_tune("scan.bps", 0);
+  const int pfd = b200_tune("scan.pfd", -1);  // L2 prefetch distance in tiles (0 = off, -1 = one wave of CTAs)
   // the warp-specialised kernel needs both Views 16-byte aligned (bulk copies); otherwise the uniform kernel
   const bool aligned = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0);
   const int ws = aligned ? b200_tune("scan.ws", 2) : 0;
@@ -38,7 +39,7 @@ int scan_entry(b200_instance* I, const char* where, const T* x, T* y, int64_t n,
 #define YCFG(BL, NV, NB, LB) \
   if (ws == 3 && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 3>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg, nseeds);
 #define XCFG(BL, NV, NB, LB) \
-  if (ws == 2 && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 2>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg, nseeds);
+  if (ws == 2 && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 2>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg, nseeds, pfd);
 #define WCFG(BL, NV, NB, LB) \
   if (ws == 1 && block == BL && nv == NV && nbuf == NB && lbw == LB) return ContigScanLaunch<T, BL, NV, NB, LB, INCL, 1>::run(I, x, y, n, seed, seed_dev, th, td, bps, sleep_ns, dbg, nseeds);
   XCFG(128, 9, 4, 1)   // shipped: 5 variants x ~90 configurations measured, profiles/r01_scan_probe_v*.log

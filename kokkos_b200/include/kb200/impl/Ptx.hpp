@@ -45,6 +45,10 @@ KB200_DEVICE_FUNCTION void bulk_g2s(void* dst_smem, const void* src_gmem, unsign
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// global -> L2 only (no destination in shared memory, nothing to wait for): SASS UBLKPF
+KB200_DEVICE_FUNCTION void bulk_prefetch_l2(const void* src_gmem, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 // shared -> global, tracked by bulk async-groups
 KB200_DEVICE_FUNCTION void bulk_s2g(void* dst_gmem, const void* src_smem, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)

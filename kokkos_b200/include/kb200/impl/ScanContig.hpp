@@ -78,6 +78,7 @@ struct ScanContigParams {
   int bulk_load, bulk_store;  // 16-byte alignment of x / y allows the TMA path
   int spin_sleep_ns;          // back-off between polls of an unpublished predecessor (0 = none)
   int dbg_flags;              // tools/sweep.py experiments only: 1 = skip look-back, 2 = skip the scan (pure copy)
+  int prefetch_tiles;         // > 0: whoever takes tile t also asks the L2 for tile t + prefetch_tiles (HBM runs ahead of the stage ring)
   // ---- multi-GPU "rounds" (block-cyclic distributed scan; csrc/comm.cu).  tpr == 0: single GPU, nothing below is used.
   int64 tpr;                  // tiles per round; a round (tpr * TILE elements) is the block of the block-cyclic distribution
   int rank, world;
@@ -567,6 +568,11 @@ __global__ void __launch_bounds__(CBLOCK + 96 + (ROUNDS ? 32 : 0)) contig_scan_w
             if (lane == 0) {
               ptx::mbar_expect_tx(&full[st], TILE_BYTES);
               ptx::bulk_g2s(buf, p.x + base, TILE_BYTES, &full[st]);
+              // L2 is shared by all SMs: it does not matter WHICH CTA will own tile t + D, so the CTA that takes tile t asks for
+              // it.  The HBM->L2 stream then runs D tiles ahead of the stage ring and the stage loads become L2 hits, which
+              // shortens the time a stage is held for its load and leaves more of the ring to cover the prefix wait.
+              const int64 ahead = base + (int64)p.prefetch_tiles * TILE;
+              if (p.prefetch_tiles > 0 && ahead + TILE <= p.n) ptx::bulk_prefetch_l2(p.x + ahead, TILE_BYTES);
             }
           } else {
             const int64 remaining = p.n - base;
@@ -848,7 +854,8 @@ struct ContigScanLaunch {
 
   // One rank of a block-cyclic distributed scan: x/y = this rank's rounds back to back (n elements), every rank runs
   // `nrounds` rounds of `tpr` tiles (tiles past n are empty but still take part in the exchange).  16-byte aligned Views.
-  static int run_rounds(b200_instance* inst, const RoundPeers& peers, int64 tpr, int64 nrounds, const T* x, T* y, int64 n, T* total_host, T* total_dev) {
+  static int run_rounds(b200_instance* inst, const RoundPeers& peers, int64 tpr, int64 nrounds, const T* x, T* y, int64 n, T* total_host, T* total_dev,
+                        int prefetch_tiles = 0) {
     static_assert(WS == 2, "the rounds kernel is the warp-specialised one");
     HostRuntime rt(inst);
     int rc;
@@ -889,6 +896,7 @@ struct ContigScanLaunch {
     p.total0 = total_host ? reinterpret_cast<T*>(slot_dev) : total_dev;
     p.total1 = total_host ? total_dev : nullptr;
     p.bulk_load = 1; p.bulk_store = 1;
+    p.prefetch_tiles = prefetch_tiles < 0 ? grid : prefetch_tiles;  // auto: one wave of CTAs ahead
     p.tpr = tpr; p.rank = peers.rank; p.world = peers.world; p.rtag_base = peers.rtag_base;
     p.rdesc = peers.rdesc; p.mbox = peers.mbox; p.racc = peers.racc;
     if (tpr > 32768) return b200_report_error(B200_EINVAL, "kb200::parallel_scan (rounds): at most 32768 tiles per round");
@@ -905,7 +913,7 @@ struct ContigScanLaunch {
   }
 
   static int run(b200_instance* inst, const T* x, T* y, int64 n, T seed, const T* seed_dev, T* total_host, T* total_dev,
-                 int blocks_per_sm_cap = 0, int spin_sleep_ns = 0, int dbg_flags = 0, int seed_count = 1) {
+                 int blocks_per_sm_cap = 0, int spin_sleep_ns = 0, int dbg_flags = 0, int seed_count = 1, int prefetch_tiles = 0) {
     HostRuntime rt(inst);
     int rc;
     if (n == 0) {  // empty range: total = identity, nothing written
@@ -940,6 +948,9 @@ struct ContigScanLaunch {
     p.bulk_store = (reinterpret_cast<uintptr_t>(y) % 16 == 0);
     p.spin_sleep_ns = spin_sleep_ns;
     p.dbg_flags = dbg_flags;
+    // auto: one wave of CTAs ahead (B200, 2^30 int64, profiles/r02_scan_prefetch_probe.log: off 6.20, 148 tiles 6.85, 222-600 tiles
+    // 6.97-7.00, 888 tiles 6.73, >= 1776 tiles (33 MB) 4.9 TB/s -- the prefetched lines are evicted before they are used)
+    p.prefetch_tiles = prefetch_tiles < 0 ? grid : prefetch_tiles;
     kernel()<<<grid, THREADS, SMEM, rt.stream()>>>(p);
     if ((rc = rt.check_launch("kb200::contig_scan_kernel"))) return rc;
     if (total_host) {
