@@ -22,6 +22,9 @@ def main():
     big = len(sys.argv) > 4 and sys.argv[4] == "big"
     space = kb.B200(rank)
     comm = kb.Comm(space, rank, world, uid)
+    for kv in os.environ.get("KB200_TUNE", "").split(","):  # e.g. KB200_TUNE=comm.agd=-1 (aggregates ahead of the data)
+        if "=" in kv:
+            kb.tune_set(kv.split("=")[0], int(kv.split("=")[1]))
     if os.environ.get("KB200_COMM_ALGO"):  # 1 = the lock-step kernel (ScanChunked.hpp) instead of the rounds kernel
         kb.tune_set("comm.scan_algo", int(os.environ["KB200_COMM_ALGO"]))
 
