@@ -162,6 +162,7 @@ int b200_finalize(b200_instance* I) {
   if (!I) return b200_set_error(B200_ENOTINIT, "b200_finalize", nullptr);
   DeviceGuard guard(I->device);
   b200_hostpath_release(I);
+  b200_spmv_release(I);
   if (I->stream || !I->owns_stream) cudaStreamSynchronize(I->stream);
   if (I->partials) cudaFree(I->partials);
   if (I->flags) cudaFree(I->flags);

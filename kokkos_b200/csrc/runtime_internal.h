@@ -55,6 +55,7 @@ struct b200_instance {
 
 int b200_set_error(int code, const char* where, const char* detail);
 void b200_hostpath_release(b200_instance* inst);  // hostpath.cu: drop the instance's staging pipeline (called by b200_finalize)
+void b200_spmv_release(b200_instance* inst);      // spmv.cu: forget the matrix metadata remembered for the instance (called by b200_finalize)
 int b200_tune(const char* key, int dflt);  // value of a tuning knob, or dflt
 
 #define B200_CHECK_INST(I, where) \

@@ -94,6 +94,20 @@ int launch(b200_instance* I, int64 nrows, const int64* row_map, const int* col_i
 }
 }  // namespace
 
+namespace {
+// (instance, row_map, nrows) -> nnz, remembered so that repeated products with one matrix do not read the row map back
+struct SpmvMeta { b200_instance* inst; const int64_t* rm; int64_t nrows, nnz; };
+SpmvMeta g_spmv_cache[8];
+int g_spmv_cache_next = 0;
+std::mutex g_spmv_cache_mu;
+}  // namespace
+
+// b200_finalize: forget what was remembered for a dying instance (a later instance may reuse the address)
+void b200_spmv_release(b200_instance* I) {
+  std::lock_guard<std::mutex> g(g_spmv_cache_mu);
+  for (SpmvMeta& m : g_spmv_cache) if (m.inst == I) m = SpmvMeta{nullptr, nullptr, 0, 0};
+}
+
 extern "C" int b200_spmv_crs_f64(b200_instance* I, int64_t nrows, const int64_t* row_map, const int32_t* col_idx,
                                  const double* values, const double* x, double* y) {
   const char* where = "b200_spmv_crs_f64";
@@ -105,14 +119,10 @@ extern "C" int b200_spmv_crs_f64(b200_instance* I, int64_t nrows, const int64_t*
   // query in the reference's terms (Crs::numRows / nnz).  Reading it back costs a stream synchronisation, so the answer is
   // remembered per (instance, row_map, nrows): repeated products with the same matrix launch without touching the host.
   // The choice only affects speed -- every vector length is correct for every row length.
-  struct Meta { b200_instance* inst; const int64_t* rm; int64_t nrows, nnz; };
-  static Meta cache[8];
-  static int cache_next = 0;
-  static std::mutex cache_mu;
   int64 nnz = -1;
   {
-    std::lock_guard<std::mutex> g(cache_mu);
-    for (const Meta& m : cache) if (m.inst == I && m.rm == row_map && m.nrows == nrows) nnz = m.nnz;
+    std::lock_guard<std::mutex> g(g_spmv_cache_mu);
+    for (const SpmvMeta& m : g_spmv_cache) if (m.inst == I && m.rm == row_map && m.nrows == nrows) nnz = m.nnz;
   }
   if (nnz < 0) {
     int64_t ends[2] = {0, 0};
@@ -121,9 +131,9 @@ extern "C" int b200_spmv_crs_f64(b200_instance* I, int64_t nrows, const int64_t*
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)b200_instance_stream(I));
     if (e != cudaSuccess) return b200_set_error((int)e, where, "row_map read-back");
     nnz = ends[1] - ends[0];
-    std::lock_guard<std::mutex> g(cache_mu);
-    cache[cache_next] = Meta{I, row_map, nrows, nnz};
-    cache_next = (cache_next + 1) % 8;
+    std::lock_guard<std::mutex> g(g_spmv_cache_mu);
+    g_spmv_cache[g_spmv_cache_next] = SpmvMeta{I, row_map, nrows, nnz};
+    g_spmv_cache_next = (g_spmv_cache_next + 1) % 8;
   }
   if (nnz > 0 && (!col_idx || !values || !x)) return b200_set_error(B200_EINVAL, where, "NULL array");
   int vl = b200_tune("spmv.vl", 0);
