@@ -404,7 +404,7 @@ class Bench:
     def roofline(self):
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_scan_ncu_summary.json"))).get("dram_bytes_per_launch_at_2^30")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_scan_ncu_summary.json"))).get("dram_bytes_per_launch_at_2^30")
         except Exception:
             pass
         achieved = 16.0 * self.n_local / (self.scan_ms * 1e-3) / 1e9
