@@ -41,9 +41,25 @@
 #include <Kokkos_B200.hpp>
 
 #include <iosfwd>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 
 namespace Kokkos {
+
+namespace Impl {
+namespace B200Adapter {
+inline std::map<const void*, std::shared_ptr<Kokkos::Cuda>>& cuda_companions() {
+  static std::map<const void*, std::shared_ptr<Kokkos::Cuda>> companions;
+  return companions;
+}
+inline std::mutex& cuda_companions_mutex() {
+  static std::mutex m;
+  return m;
+}
+}  // namespace B200Adapter
+}  // namespace Impl
 
 class B200 {
  public:
@@ -66,7 +82,13 @@ class B200 {
     else if (settings.has_device_id()) device = settings.get_device_id();
     kb200::initialize(kb200::InitializationSettings().set_device_id(device));
   }
-  static void impl_finalize() { kb200::finalize(); }
+  static void impl_finalize() {
+    {
+      std::lock_guard<std::mutex> lock(Impl::B200Adapter::cuda_companions_mutex());
+      Impl::B200Adapter::cuda_companions().clear();
+    }
+    kb200::finalize();
+  }
   static int impl_is_initialized() { return kb200::is_initialized() ? 1 : 0; }
   static void impl_static_fence(const std::string& name) {
     Kokkos::Tools::Experimental::Impl::profile_fence_event<B200>(
@@ -83,6 +105,17 @@ class B200 {
   cudaStream_t cuda_stream() const { return m_space.cuda_stream(); }
   int cuda_device() const { return m_space.cuda_device(); }
   const kb200::B200& impl_kb200() const { return m_space; }
+  // Views in CudaSpace that are allocated, zero-filled or copied "on" this instance (view_alloc(label, exec), the execution-space
+  // overloads of deep_copy) go through the reference's CudaSpace / DeepCopy, whose overloads take a Kokkos::Cuda
+  // (Cuda/Kokkos_CudaSpace.hpp:83-86,476-478): hand them one that wraps the SAME stream, created on first use
+  // (an execution space object may not be larger than two pointers, impl/Kokkos_ExecSpaceManager.hpp:105, so the companion lives in a
+  // registry keyed by the instance; impl_finalize() drops it before the reference finalizes its Cuda space)
+  operator const Kokkos::Cuda&() const {
+    std::lock_guard<std::mutex> lock(Impl::B200Adapter::cuda_companions_mutex());
+    std::shared_ptr<Kokkos::Cuda>& slot = Impl::B200Adapter::cuda_companions()[(const void*)m_space.impl_instance()];
+    if (!slot || slot->cuda_stream() != cuda_stream()) slot = std::make_shared<Kokkos::Cuda>(cuda_stream());
+    return *slot;
+  }
 
  private:
   friend bool operator==(B200 const& a, B200 const& b) { return a.m_space == b.m_space; }

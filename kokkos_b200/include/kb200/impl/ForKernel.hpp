@@ -19,7 +19,7 @@ namespace kb200 {
 namespace Impl {
 
 template <class Body, int BLOCK, int UNROLL>
-__global__ void __launch_bounds__(BLOCK) range_for_kernel(const __grid_constant__ Body body, const int64 n_units) {
+KB200_DEVICE_FUNCTION void range_for_tiles(const Body& body, const int64 n_units) {
   constexpr int64 TILE = (int64)BLOCK * UNROLL;
   const int64 full_tiles = n_units / TILE;
   for (int64 tile = blockIdx.x; tile < full_tiles; tile += gridDim.x) {
@@ -40,6 +40,17 @@ __global__ void __launch_bounds__(BLOCK) range_for_kernel(const __grid_constant_
   for (int64 k = (int64)blockIdx.x * BLOCK + threadIdx.x; k < edges; k += (int64)gridDim.x * BLOCK) body.edge(k);
 }
 
+template <class Body, int BLOCK, int UNROLL>
+__global__ void __launch_bounds__(BLOCK) range_for_kernel(const __grid_constant__ Body body, const int64 n_units) {
+  range_for_tiles<Body, BLOCK, UNROLL>(body, n_units);
+}
+// closures beyond the kernel parameter space (the reference's "global memory launch", Cuda/Kokkos_Cuda_KernelLaunch.hpp:317-420):
+// the closure is copied into the instance's functor scratch in stream order and the kernel reads it from there
+template <class Body, int BLOCK, int UNROLL>
+__global__ void __launch_bounds__(BLOCK) range_for_kernel_global(const Body* __restrict__ body, const int64 n_units) {
+  range_for_tiles<Body, BLOCK, UNROLL>(*body, n_units);
+}
+
 template <class Body, int BLOCK = 256, int UNROLL = 4>
 struct RangeForLaunch {
   static int resident_blocks_per_sm() {
@@ -47,7 +58,8 @@ struct RangeForLaunch {
     int& cached = cache.here();
     if (cached == 0) {
       int nb = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, range_for_kernel<Body, BLOCK, UNROLL>, BLOCK, 0);
+      if constexpr (sizeof(Body) > 32000) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, range_for_kernel_global<Body, BLOCK, UNROLL>, BLOCK, 0);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, range_for_kernel<Body, BLOCK, UNROLL>, BLOCK, 0);
       cached = nb > 0 ? nb : 1;
     }
     return cached;
@@ -57,9 +69,9 @@ struct RangeForLaunch {
   // what a fixed tile->block assignment cannot when iterations differ in latency (random atomics: the last blocks of a one-wave grid
   // finish 9% late -- profiles/r02_for_waves.log).
   static int run(b200_instance* inst, const Body& body, int64 n_units, int blocks_per_sm_cap = 0, int waves = 1) {
-    static_assert(sizeof(Body) <= 32000, "closure exceeds the kernel parameter space");
     HostRuntime rt(inst);
     constexpr int64 TILE = (int64)BLOCK * UNROLL;
+    constexpr bool kGlobal = sizeof(Body) > 32000;  // beyond the kernel parameter space (32 764 bytes on sm_100)
     int64 tiles = (n_units + TILE - 1) / TILE;
     if (tiles < 1) {
       if (body.edge_count() == 0) return 0;  // empty range: nothing to launch
@@ -73,7 +85,15 @@ struct RangeForLaunch {
       if (grid > cap) grid = cap;
     }
     if (grid > 0x7fffffffll) grid = 0x7fffffffll;
-    range_for_kernel<Body, BLOCK, UNROLL><<<(unsigned)grid, BLOCK, 0, rt.stream()>>>(body, n_units);
+    if constexpr (kGlobal) {
+      void* dev = nullptr;
+      int rc;
+      if ((rc = b200_scratch_get(inst, B200_SCRATCH_FUNCTOR, sizeof(Body), &dev, nullptr))) return rc;
+      if ((rc = b200_memcpy_h2d_async(inst, dev, &body, sizeof(Body)))) return rc;  // pageable source: staged before the call returns
+      range_for_kernel_global<Body, BLOCK, UNROLL><<<(unsigned)grid, BLOCK, 0, rt.stream()>>>(reinterpret_cast<const Body*>(dev), n_units);
+    } else {
+      range_for_kernel<Body, BLOCK, UNROLL><<<(unsigned)grid, BLOCK, 0, rt.stream()>>>(body, n_units);
+    }
     return rt.check_launch("kb200::range_for_kernel");
   }
 };

@@ -832,3 +832,27 @@ extern "C" int kb200_case_array_reduce_big(i64 n, int count, i64 n0, i64 n1, i64
     return 0;
   });
 }
+
+// ---- a closure larger than the kernel parameter space (32 764 bytes): the reference's "global memory launch"
+// (Cuda/Kokkos_Cuda_KernelLaunch.hpp:317-420; core/unit_test/TestGraph.hpp:423-445 builds such a functor)
+namespace {
+struct HugeClosure {
+  View<i64*> out;
+  unsigned char ballast[40000];
+  KB200_INLINE_FUNCTION void operator()(const i64 i) const { out(i) = i * 3 + (i64)ballast[i % 40000]; }
+};
+}  // namespace
+extern "C" int kb200_case_huge_closure(i64 n, i64* checksum) {
+  return guarded([&] {
+    static_assert(sizeof(HugeClosure) > 32764, "must not fit the kernel parameter space");
+    View<i64*> out("out", (size_t)n);
+    auto f = std::make_unique<HugeClosure>();
+    f->out = out;
+    for (int k = 0; k < 40000; ++k) f->ballast[k] = (unsigned char)(k * 7 + 1);
+    parallel_for("huge closure", RangePolicy<>(0, n), *f);
+    i64 s = 0;
+    parallel_reduce("check", RangePolicy<>(0, n), KB200_LAMBDA(const i64 i, i64& u) { u += out(i); }, s);
+    *checksum = s;
+    return 0;
+  });
+}

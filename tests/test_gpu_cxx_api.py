@@ -315,3 +315,14 @@ def test_runtime_length_array_reduce_of_any_length(cases, count):
     np.add.at(exp_m, ((ii * 7 + jj) % count).ravel(), (1 + jj).ravel())
     exp_m[0] += 1000000
     assert np.array_equal(out_m, exp_m)
+
+
+def test_closure_larger_than_the_kernel_parameter_space(cases):
+    """A 40 KB functor cannot be a kernel argument: parallel_for copies it into the instance's functor scratch in stream order and
+    the kernel reads it from global memory (the reference's 'global memory launch')."""
+    n = 100003
+    out = c_int64()
+    ok(cases, cases.kb200_case_huge_closure(c_int64(n), ctypes.byref(out)))
+    i = np.arange(n, dtype=np.int64)
+    ballast = ((np.arange(40000, dtype=np.int64) * 7 + 1) % 256)
+    assert out.value == int((i * 3 + ballast[i % 40000]).sum())
