@@ -17,9 +17,26 @@
 // shuffle/redux + ordered ticket combine, single-pass look-back scan): each specialisation only translates the reference's
 // policy and functor/reducer into the kernel-side "Body"/"Red" concepts and launches through libkokkos_b200.so.
 // Memory: Kokkos::CudaSpace (the reference's), so every View type of a Cuda build works unchanged.
-// TeamPolicy: Kokkos_B200_Team.hpp.  Not provided yet: TeamThreadMDRange / ThreadVectorMDRange / TeamVectorMDRange.
+// TeamPolicy and the nested Team*MDRange policies: Kokkos_B200_Team.hpp.
 #ifndef KOKKOS_B200_SPACE_HPP
 #define KOKKOS_B200_SPACE_HPP
+
+#ifdef KB200_AS_KOKKOS
+#error "the adapter uses the kb200:: layer under its own name; do not define KB200_AS_KOKKOS here"
+#endif
+// The kernel layer first (it is self-contained), so that the forwarding overloads of the nested patterns can be DECLARED before the
+// reference's headers are parsed: impl/Kokkos_TeamMDPolicy.hpp calls parallel_for / parallel_reduce unqualified from inside
+// namespace Kokkos::Impl on whatever TeamThreadRange(team, n) returns, and only names already declared at that point (or found
+// by argument-dependent lookup, which does not reach namespace Kokkos for kb200 types) are considered.
+#include <Kokkos_B200.hpp>
+namespace Kokkos {
+template <class Range, class L, std::enable_if_t<kb200::Impl::is_nested_range<Range>::value, int> = 0>
+KB200_TEAM_FUNCTION void parallel_for(const Range& r, const L& f);
+template <class Range, class L, class... R, std::enable_if_t<kb200::Impl::is_nested_range<Range>::value, int> = 0>
+KB200_TEAM_FUNCTION void parallel_reduce(const Range& r, const L& f, R&&... result);
+template <class Range, class L, class... R, std::enable_if_t<kb200::Impl::is_nested_range<Range>::value, int> = 0>
+KB200_TEAM_FUNCTION void parallel_scan(const Range& r, const L& f, R&&... result);
+}  // namespace Kokkos
 
 #include <Kokkos_Core.hpp>
 // a backend header: allowed to see the reference's implementation headers (as its own backends do)
@@ -35,10 +52,6 @@
 #if !defined(KOKKOS_ENABLE_CUDA)
 #error "Kokkos::B200 needs a CUDA-enabled build of Kokkos (it reuses Kokkos::CudaSpace and the CUDA function annotations)"
 #endif
-#ifdef KB200_AS_KOKKOS
-#error "the adapter uses the kb200:: layer under its own name; do not define KB200_AS_KOKKOS here"
-#endif
-#include <Kokkos_B200.hpp>
 
 #include <iosfwd>
 #include <map>

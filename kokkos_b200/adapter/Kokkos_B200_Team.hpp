@@ -266,6 +266,11 @@ class ParallelReduce<CombinedFunctorReducerType, Kokkos::TeamPolicy<Properties..
   const bool m_result_ptr_device_accessible;
 };
 
+// TeamThreadMDRange / ThreadVectorMDRange / TeamVectorMDRange: the reference's generic nested-loop machinery (impl/Kokkos_TeamMDPolicy.hpp)
+// only needs to know on which nest levels to parallelise; as on the reference's GPU backends (Cuda/Kokkos_Cuda_MDRangePolicy.hpp:52-55)
+template <typename Rank, TeamMDRangeThreadAndVector ThreadAndVector>
+struct ThreadAndVectorNestLevel<Rank, Kokkos::B200, ThreadAndVector> : AcceleratorBasedNestLevel<Rank, ThreadAndVector> {};
+
 }  // namespace Impl
 
 // ---- nested policies and patterns on the B200 team handle: the kernel layer's own, under the names a Kokkos user writes ----
@@ -284,12 +289,35 @@ KOKKOS_INLINE_FUNCTION auto ThreadVectorRange(const Impl::B200AdapterTeamMember&
 KOKKOS_INLINE_FUNCTION auto PerTeam(const Impl::B200AdapterTeamMember& m) { return kb200::PerTeam(m); }
 KOKKOS_INLINE_FUNCTION auto PerThread(const Impl::B200AdapterTeamMember& m) { return kb200::PerThread(m); }
 
-template <class Range, class L, std::enable_if_t<kb200::Impl::is_nested_range<Range>::value, int> = 0>
-KOKKOS_INLINE_FUNCTION void parallel_for(const Range& r, const L& f) { kb200::parallel_for(r, f); }
-template <class Range, class L, class... R, std::enable_if_t<kb200::Impl::is_nested_range<Range>::value, int> = 0>
-KOKKOS_INLINE_FUNCTION void parallel_reduce(const Range& r, const L& f, R&&... result) { kb200::parallel_reduce(r, f, static_cast<R&&>(result)...); }
-template <class Range, class L, class... R, std::enable_if_t<kb200::Impl::is_nested_range<Range>::value, int> = 0>
-KOKKOS_INLINE_FUNCTION void parallel_scan(const Range& r, const L& f, R&&... result) { kb200::parallel_scan(r, f, static_cast<R&&>(result)...); }
+// (declared at the top of Kokkos_B200_Space.hpp, before the reference's headers)
+template <class Range, class L, std::enable_if_t<kb200::Impl::is_nested_range<Range>::value, int>>
+KB200_TEAM_FUNCTION void parallel_for(const Range& r, const L& f) { kb200::parallel_for(r, f); }
+template <class Range, class L, class... R, std::enable_if_t<kb200::Impl::is_nested_range<Range>::value, int>>
+KB200_TEAM_FUNCTION void parallel_reduce(const Range& r, const L& f, R&&... result) { kb200::parallel_reduce(r, f, static_cast<R&&>(result)...); }
+template <class Range, class L, class... R, std::enable_if_t<kb200::Impl::is_nested_range<Range>::value, int>>
+KB200_TEAM_FUNCTION void parallel_scan(const Range& r, const L& f, R&&... result) { kb200::parallel_scan(r, f, static_cast<R&&>(result)...); }
+// Nested MDRange reductions that spread over vector lanes: the reference's generic overloads (Kokkos_ExecPolicy.hpp:1149-1214) fold the
+// lanes only for the execution spaces they list by name, so the B200 handle gets its own, more specialised pair that always folds
+// them (lanes first, then threads: team_reduce counts a thread's value once, from lane 0)
+template <typename Rank, typename Lambda, typename ReducerValueType>
+KOKKOS_INLINE_FUNCTION void parallel_reduce(ThreadVectorMDRange<Rank, Impl::B200AdapterTeamMember> const& policy, Lambda const& lambda,
+                                            ReducerValueType& val) {
+  static_assert(!std::is_array_v<ReducerValueType> && !std::is_pointer_v<ReducerValueType> && !Kokkos::is_reducer_v<ReducerValueType>,
+                "Only scalar return types are allowed!");
+  val = ReducerValueType{};
+  Impl::md_parallel_impl<Rank>(policy, lambda, val);
+  kb200::Impl::vector_reduce(kb200::Impl::NestedSum<ReducerValueType>{}, val);
+}
+template <typename Rank, typename Lambda, typename ReducerValueType>
+KOKKOS_INLINE_FUNCTION void parallel_reduce(TeamVectorMDRange<Rank, Impl::B200AdapterTeamMember> const& policy, Lambda const& lambda,
+                                            ReducerValueType& val) {
+  static_assert(!std::is_array_v<ReducerValueType> && !std::is_pointer_v<ReducerValueType> && !Kokkos::is_reducer_v<ReducerValueType>,
+                "Only scalar return types are allowed!");
+  val = ReducerValueType{};
+  Impl::md_parallel_impl<Rank>(policy, lambda, val);
+  kb200::Impl::vector_reduce(kb200::Impl::NestedSum<ReducerValueType>{}, val);
+  policy.team.team_reduce(kb200::Impl::NestedSum<ReducerValueType>{}, val);
+}
 template <class L>
 KOKKOS_INLINE_FUNCTION void single(const kb200::Impl::VectorSingleStruct& s, const L& f) { kb200::single(s, f); }
 template <class L>
