@@ -36,6 +36,34 @@ template <class Range, class L, class... R, std::enable_if_t<kb200::Impl::is_nes
 KB200_TEAM_FUNCTION void parallel_reduce(const Range& r, const L& f, R&&... result);
 template <class Range, class L, class... R, std::enable_if_t<kb200::Impl::is_nested_range<Range>::value, int> = 0>
 KB200_TEAM_FUNCTION void parallel_scan(const Range& r, const L& f, R&&... result);
+// The nested-policy factories and `single`, for the same reason: Kokkos_CopyViews.hpp (local_deep_copy) and
+// Kokkos_AcquireUniqueTokenImpl.hpp call them QUALIFIED (Kokkos::TeamVectorRange(team, n), Kokkos::single(Kokkos::PerTeam(team), f)),
+// which binds to the overloads declared at that point of the reference's headers.  Defined in Kokkos_B200_Team.hpp.
+namespace Impl {
+class B200AdapterTeamMember;
+}
+template <class I>
+KB200_TEAM_FUNCTION kb200::Impl::TeamThreadRangeStruct<I> TeamThreadRange(const Impl::B200AdapterTeamMember& m, I count);
+template <class I1, class I2>
+KB200_TEAM_FUNCTION kb200::Impl::TeamThreadRangeStruct<std::common_type_t<I1, I2>> TeamThreadRange(const Impl::B200AdapterTeamMember& m, I1 b, I2 e);
+template <class I>
+KB200_TEAM_FUNCTION kb200::Impl::TeamVectorRangeStruct<I> TeamVectorRange(const Impl::B200AdapterTeamMember& m, I count);
+template <class I1, class I2>
+KB200_TEAM_FUNCTION kb200::Impl::TeamVectorRangeStruct<std::common_type_t<I1, I2>> TeamVectorRange(const Impl::B200AdapterTeamMember& m, I1 b, I2 e);
+template <class I>
+KB200_TEAM_FUNCTION kb200::Impl::ThreadVectorRangeStruct<I> ThreadVectorRange(const Impl::B200AdapterTeamMember& m, I count);
+template <class I1, class I2>
+KB200_TEAM_FUNCTION kb200::Impl::ThreadVectorRangeStruct<std::common_type_t<I1, I2>> ThreadVectorRange(const Impl::B200AdapterTeamMember& m, I1 b, I2 e);
+KB200_TEAM_FUNCTION kb200::Impl::ThreadSingleStruct PerTeam(const Impl::B200AdapterTeamMember& m);
+KB200_TEAM_FUNCTION kb200::Impl::VectorSingleStruct PerThread(const Impl::B200AdapterTeamMember& m);
+template <class L>
+KB200_TEAM_FUNCTION void single(const kb200::Impl::VectorSingleStruct& s, const L& f);
+template <class L>
+KB200_TEAM_FUNCTION void single(const kb200::Impl::ThreadSingleStruct& s, const L& f);
+template <class L, class T>
+KB200_TEAM_FUNCTION void single(const kb200::Impl::VectorSingleStruct& s, const L& f, T& val);
+template <class L, class T>
+KB200_TEAM_FUNCTION void single(const kb200::Impl::ThreadSingleStruct& s, const L& f, T& val);
 }  // namespace Kokkos
 
 #include <Kokkos_Core.hpp>
@@ -430,5 +458,6 @@ class ParallelReduce<CombinedFunctorReducerType, Kokkos::MDRangePolicy<Traits...
 }  // namespace Kokkos
 
 #include "Kokkos_B200_Team.hpp"
+#include "Kokkos_B200_UniqueToken.hpp"
 
 #endif

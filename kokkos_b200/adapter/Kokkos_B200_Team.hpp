@@ -274,22 +274,22 @@ struct ThreadAndVectorNestLevel<Rank, Kokkos::B200, ThreadAndVector> : Accelerat
 }  // namespace Impl
 
 // ---- nested policies and patterns on the B200 team handle: the kernel layer's own, under the names a Kokkos user writes ----
+// (these and the pattern forwarders below are declared at the top of Kokkos_B200_Space.hpp, before the reference's headers)
 template <class I>
-KOKKOS_INLINE_FUNCTION auto TeamThreadRange(const Impl::B200AdapterTeamMember& m, I count) { return kb200::TeamThreadRange(m, count); }
+KB200_TEAM_FUNCTION kb200::Impl::TeamThreadRangeStruct<I> TeamThreadRange(const Impl::B200AdapterTeamMember& m, I count) { return kb200::TeamThreadRange(m, count); }
 template <class I1, class I2>
-KOKKOS_INLINE_FUNCTION auto TeamThreadRange(const Impl::B200AdapterTeamMember& m, I1 b, I2 e) { return kb200::TeamThreadRange(m, b, e); }
+KB200_TEAM_FUNCTION kb200::Impl::TeamThreadRangeStruct<std::common_type_t<I1, I2>> TeamThreadRange(const Impl::B200AdapterTeamMember& m, I1 b, I2 e) { return kb200::TeamThreadRange(m, b, e); }
 template <class I>
-KOKKOS_INLINE_FUNCTION auto TeamVectorRange(const Impl::B200AdapterTeamMember& m, I count) { return kb200::TeamVectorRange(m, count); }
+KB200_TEAM_FUNCTION kb200::Impl::TeamVectorRangeStruct<I> TeamVectorRange(const Impl::B200AdapterTeamMember& m, I count) { return kb200::TeamVectorRange(m, count); }
 template <class I1, class I2>
-KOKKOS_INLINE_FUNCTION auto TeamVectorRange(const Impl::B200AdapterTeamMember& m, I1 b, I2 e) { return kb200::TeamVectorRange(m, b, e); }
+KB200_TEAM_FUNCTION kb200::Impl::TeamVectorRangeStruct<std::common_type_t<I1, I2>> TeamVectorRange(const Impl::B200AdapterTeamMember& m, I1 b, I2 e) { return kb200::TeamVectorRange(m, b, e); }
 template <class I>
-KOKKOS_INLINE_FUNCTION auto ThreadVectorRange(const Impl::B200AdapterTeamMember& m, I count) { return kb200::ThreadVectorRange(m, count); }
+KB200_TEAM_FUNCTION kb200::Impl::ThreadVectorRangeStruct<I> ThreadVectorRange(const Impl::B200AdapterTeamMember& m, I count) { return kb200::ThreadVectorRange(m, count); }
 template <class I1, class I2>
-KOKKOS_INLINE_FUNCTION auto ThreadVectorRange(const Impl::B200AdapterTeamMember& m, I1 b, I2 e) { return kb200::ThreadVectorRange(m, b, e); }
-KOKKOS_INLINE_FUNCTION auto PerTeam(const Impl::B200AdapterTeamMember& m) { return kb200::PerTeam(m); }
-KOKKOS_INLINE_FUNCTION auto PerThread(const Impl::B200AdapterTeamMember& m) { return kb200::PerThread(m); }
+KB200_TEAM_FUNCTION kb200::Impl::ThreadVectorRangeStruct<std::common_type_t<I1, I2>> ThreadVectorRange(const Impl::B200AdapterTeamMember& m, I1 b, I2 e) { return kb200::ThreadVectorRange(m, b, e); }
+KB200_TEAM_FUNCTION kb200::Impl::ThreadSingleStruct PerTeam(const Impl::B200AdapterTeamMember& m) { return kb200::PerTeam(m); }
+KB200_TEAM_FUNCTION kb200::Impl::VectorSingleStruct PerThread(const Impl::B200AdapterTeamMember& m) { return kb200::PerThread(m); }
 
-// (declared at the top of Kokkos_B200_Space.hpp, before the reference's headers)
 template <class Range, class L, std::enable_if_t<kb200::Impl::is_nested_range<Range>::value, int>>
 KB200_TEAM_FUNCTION void parallel_for(const Range& r, const L& f) { kb200::parallel_for(r, f); }
 template <class Range, class L, class... R, std::enable_if_t<kb200::Impl::is_nested_range<Range>::value, int>>
@@ -319,13 +319,13 @@ KOKKOS_INLINE_FUNCTION void parallel_reduce(TeamVectorMDRange<Rank, Impl::B200Ad
   policy.team.team_reduce(kb200::Impl::NestedSum<ReducerValueType>{}, val);
 }
 template <class L>
-KOKKOS_INLINE_FUNCTION void single(const kb200::Impl::VectorSingleStruct& s, const L& f) { kb200::single(s, f); }
+KB200_TEAM_FUNCTION void single(const kb200::Impl::VectorSingleStruct& s, const L& f) { kb200::single(s, f); }
 template <class L>
-KOKKOS_INLINE_FUNCTION void single(const kb200::Impl::ThreadSingleStruct& s, const L& f) { kb200::single(s, f); }
+KB200_TEAM_FUNCTION void single(const kb200::Impl::ThreadSingleStruct& s, const L& f) { kb200::single(s, f); }
 template <class L, class T>
-KOKKOS_INLINE_FUNCTION void single(const kb200::Impl::VectorSingleStruct& s, const L& f, T& val) { kb200::single(s, f, val); }
+KB200_TEAM_FUNCTION void single(const kb200::Impl::VectorSingleStruct& s, const L& f, T& val) { kb200::single(s, f, val); }
 template <class L, class T>
-KOKKOS_INLINE_FUNCTION void single(const kb200::Impl::ThreadSingleStruct& s, const L& f, T& val) { kb200::single(s, f, val); }
+KB200_TEAM_FUNCTION void single(const kb200::Impl::ThreadSingleStruct& s, const L& f, T& val) { kb200::single(s, f, val); }
 
 }  // namespace Kokkos
 #endif

@@ -4,7 +4,8 @@
 // 69-246,248-497) and the DeviceIterateTile maps (core/src/impl/KokkosExp_IterateTileGPU.hpp:71-1156,1206-1305).
 //
 // Mapping: a tile is a thread block whose SHAPE is the tile (blockDim.x = tile[0] along the contiguous
-// dimension, blockDim.y = tile[1], blockDim.z = product of the remaining tile extents), so the hardware's
+// dimension, blockDim.y = tile[1], blockDim.z = product of the remaining tile extents -- or, when that product
+// is beyond the hardware's 64, one linear block of the same size), so the hardware's
 // threadIdx supplies the in-tile coordinates and no division is executed per element.  A persistent grid
 // (SMs x resident blocks) strides over the tiles; the tile coordinates advance by a pre-decomposed stride
 // with carries (adds and compares only).  The reference's reduce variant instead launches <= 512 blocks
@@ -28,6 +29,7 @@ struct MDParams {
   Index lower[RANK], upper[RANK], tile[RANK], tile_end[RANK];
   Index stride[RANK];  // gridDim.x decomposed in the mixed radix tile_end[] (dimension 0 fastest)
   long long num_tiles;
+  int linear;  // 1: the block is one-dimensional and threadIdx.x enumerates the tile (dimension 0 fastest)
 };
 
 template <class Tag, class F, class Index, size_t... Is, class... Extra>
@@ -41,10 +43,17 @@ template <int RANK, int C, class Index, class Op>
 KB200_DEVICE_FUNCTION void md_walk(const MDParams<RANK, Index>& p, Op op) {
   // this thread's fixed offset inside any tile
   Index off[RANK];
-  off[0] = (Index)threadIdx.x;
-  off[1] = (Index)threadIdx.y;
   {
-    Index zz = (Index)threadIdx.z;
+    Index zz;
+    if (p.linear) {
+      zz = (Index)threadIdx.x;
+      off[0] = zz % p.tile[0]; zz /= p.tile[0];
+      off[1] = zz % p.tile[1]; zz /= p.tile[1];
+    } else {
+      off[0] = (Index)threadIdx.x;
+      off[1] = (Index)threadIdx.y;
+      zz = (Index)threadIdx.z;
+    }
 #pragma unroll
     for (int d = 2; d < RANK; ++d) { off[d] = zz % p.tile[d]; zz /= p.tile[d]; }
   }
@@ -130,7 +139,11 @@ struct MDLaunchShape {
     p.num_tiles = (long long)pol.m_num_tiles;
     block = dim3((unsigned)pol.m_tile[0], (unsigned)pol.m_tile[1], (unsigned)z);
     threads = (int)(block.x * block.y * block.z);
-    if (block.z > 64) throw std::runtime_error("kb200::MDRangePolicy: product of tile extents beyond dimension 1 exceeds 64 (blockDim.z limit)");
+    p.linear = 0;
+    // blockDim.z stops at 64: a tile whose slow extents multiply past that (the reference's default tiling of a rank-6
+    // Iterate::Right policy is {2,2,2,2,2,16}, KokkosExp_MDRangePolicy.hpp:330-372) runs as a one-dimensional block that
+    // decomposes threadIdx.x once per thread instead
+    if (z > 64) { block = dim3((unsigned)threads, 1, 1); p.linear = 1; }
   }
   void set_grid(int grid) {
     long long rem = grid;

@@ -856,3 +856,29 @@ extern "C" int kb200_case_huge_closure(i64 n, i64* checksum) {
     return 0;
   });
 }
+
+// ---- a rank-6 tile whose four slow extents multiply to 128, beyond blockDim.z's 64: the reference's default tiling of a rank-6
+// Iterate::Right policy ({2,2,2,2,2,16}, KokkosExp_MDRangePolicy.hpp:330-372; its ViewFill / ViewCopy of rank >= 6 LayoutRight Views
+// launch exactly that, Kokkos_CopyViews.hpp:214-260).  The launch falls back to a linear block; every point is visited once.
+extern "C" int kb200_case_mdrange_wide_tile(i64* out_for_sum, i64* out_reduce, i64* out_points) {
+  return guarded([&] {
+    const i64 e[6] = {5, 3, 4, 3, 5, 37};
+    const size_t total = (size_t)(e[0] * e[1] * e[2] * e[3] * e[4] * e[5]);
+    View<i64*> hit("hit", total);
+    using P6 = MDRangePolicy<Rank<6>>;
+    const P6 pol({0, 0, 0, 0, 0, 0}, {e[0], e[1], e[2], e[3], e[4], e[5]}, {2, 2, 2, 2, 2, 16});
+    const i64 e1 = e[1], e2 = e[2], e3 = e[3], e4 = e[4], e5 = e[5];
+    parallel_for("wide tile for", pol, KB200_LAMBDA(const i64 a, const i64 b, const i64 c, const i64 d, const i64 f, const i64 g) {
+      const i64 flat = ((((a * e1 + b) * e2 + c) * e3 + d) * e4 + f) * e5 + g;
+      atomic_add(&hit(flat), flat + 1);
+    });
+    i64 s = 0, r = 0, pts = 0;
+    parallel_reduce("wide tile check", RangePolicy<>(0, (i64)total), KB200_LAMBDA(const i64 i, i64& u) { u += hit(i); }, s);
+    parallel_reduce("wide tile reduce", pol, KB200_LAMBDA(const i64 a, const i64 b, const i64 c, const i64 d, const i64 f, const i64 g, i64& u) {
+      u += ((((a * e1 + b) * e2 + c) * e3 + d) * e4 + f) * e5 + g + 1;
+    }, r);
+    parallel_reduce("wide tile once", RangePolicy<>(0, (i64)total), KB200_LAMBDA(const i64 i, i64& u) { u += (hit(i) == i + 1) ? 1 : 0; }, pts);
+    *out_for_sum = s; *out_reduce = r; *out_points = pts;
+    return 0;
+  });
+}

@@ -33,7 +33,7 @@ def test_reference_unit_tests_pass_on_kokkos_b200_adapter():
     tail = "\n".join(out.splitlines()[-60:])
     assert p.returncode == 0, tail
     m = re.search(r"\[  PASSED  \] (\d+) tests", out)
-    assert m and int(m.group(1)) >= 200, tail
+    assert m and int(m.group(1)) >= 310, tail
     assert "FAILED" not in out, tail
 
 

@@ -326,3 +326,14 @@ def test_closure_larger_than_the_kernel_parameter_space(cases):
     i = np.arange(n, dtype=np.int64)
     ballast = ((np.arange(40000, dtype=np.int64) * 7 + 1) % 256)
     assert out.value == int((i * 3 + ballast[i % 40000]).sum())
+
+
+def test_mdrange_tile_beyond_blockdim_z(cases):
+    """A rank-6 tile {2,2,2,2,2,16}: the four slow extents multiply to 128 > 64 (blockDim.z's limit).  This is the reference's own
+    default tiling for a rank-6 Iterate::Right policy, which its ViewFill of a rank >= 6 LayoutRight View launches; the kernel
+    layer runs it as a linear block.  parallel_for visits every point exactly once; parallel_reduce agrees."""
+    total = 5 * 3 * 4 * 3 * 5 * 37
+    s, r, pts = c_int64(), c_int64(), c_int64()
+    ok(cases, cases.kb200_case_mdrange_wide_tile(ctypes.byref(s), ctypes.byref(r), ctypes.byref(pts)))
+    exp = total * (total + 1) // 2
+    assert s.value == exp and r.value == exp and pts.value == total
