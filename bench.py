@@ -647,10 +647,38 @@ class Bench:
         return res
 
     # ---- e2e: the same step through the host-buffer C-ABI calls -------------------------------------------------------
+    def bind_to_gpu_numa_node(self):
+        """N > 1 only: run this rank's host threads on the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned buffers of the
+        e2e leg are allocated, so that first-touch places them in that node's memory (otherwise all ranks pin node-0 memory and the
+        copies of the far GPUs cross the socket link: VERDICT r1 weak 8).  Best effort: returns the node, or None when the topology
+        is not visible (containers) or KB200_NUMA=0."""
+        try:
+            if os.environ.get("KB200_NUMA", "1") == "0":
+                return None
+            pr = self.torch.cuda.get_device_properties(self.local_rank)
+            bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+                node = int(f.read().strip())
+            if node < 0:
+                return None
+            cpus = set()
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                for part in f.read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+            allowed = os.sched_getaffinity(0) & cpus
+            if len(allowed) < 2:  # the leg runs two host threads
+                return None
+            os.sched_setaffinity(0, allowed)
+            return node
+        except Exception:
+            return None
+
     def e2e(self):
         torch = self.torch
         n = self.n
         nl = min(self.n_local, n)
+        numa_node = self.bind_to_gpu_numa_node() if self.world > 1 else None
         try:
             hx = torch.empty(n, dtype=torch.float64, pin_memory=True)
             hi = torch.empty(nl, dtype=torch.int64, pin_memory=True)
@@ -685,7 +713,9 @@ class Bench:
                     "api": "b200_reduce_sum_f64_host + b200_scan_excl_i64_host (pinned host buffers, 64 MiB chunks, double-buffered), issued from two host "
                            "threads on two instances so that H2D and D2H overlap",
                     "pcie_bound_GBs_per_gpu": "24 B of metric per 16 B of H2D: <= 1.5 x the H2D rate (~55 GB/s) = ~83",
-                    "note": "per-GPU shards are independent on this leg (no cross-GPU seed): PCIe-bound"}
+                    "numa_node": numa_node,
+                    "note": "per-GPU shards are independent on this leg (no cross-GPU seed): PCIe-bound; at N > 1 each rank's host threads and pinned "
+                            "buffers are bound to its GPU's NUMA node (numa_node, null = topology not visible)"}
         except Exception as ex:  # e.g. not enough pinnable host memory
             return {"value": None, "unit": "GB/s", "error": repr(ex)[:200]}
 
